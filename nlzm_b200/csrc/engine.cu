@@ -1,0 +1,647 @@
+// Engine: owns the HBM-resident input, the work buffers and two result slots; runs the stages
+// S (suffix ranks) -> T (BT4 divide and conquer) -> H (HT2/HT3) -> R (RK256) -> M (merge) for a
+// range of positions and exposes the C ABI of include/nlzm_mf.h.
+#include "../../include/nlzm_mf.h"
+#include "platform.cuh"
+#ifdef NLZM_EMU
+#include "emu_runtime.hpp"
+#endif
+#include "common.cuh"
+#include "prim.cuh"
+#include "suffix_rank.cuh"
+#include "dc_levels.cuh"
+#include "bt_short.cuh"
+#include "ht_rows.cuh"
+#include "rk256.cuh"
+#include "merge_steps.cuh"
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include <stdio.h>
+
+// ---- launch accounting / per-kernel timing ----------------------------------------------------
+static std::atomic<unsigned long long> g_launches{0};
+struct KernelProf {
+    struct Pending { const char *name; cudaEvent_t a, b; };
+    bool on = false;
+    std::mutex mu;
+    std::vector<Pending> pending;
+    std::map<std::string, std::pair<u64, double>> acc;     // name -> (launches, ms)
+    void resolve() {                                        // call after the stream is synchronized
+        std::lock_guard<std::mutex> l(mu);
+        for (auto &p : pending) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, p.a, p.b);
+            auto &e = acc[p.name];
+            e.first += 1;
+            e.second += ms;
+            cudaEventDestroy(p.a);
+            cudaEventDestroy(p.b);
+        }
+        pending.clear();
+    }
+};
+static KernelProf g_prof;
+void nlzm_launch_begin(const char *name, cudaStream_t st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof.on) return;
+    KernelProf::Pending p;
+    p.name = name;
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+    cudaEventRecord(p.a, st);
+    std::lock_guard<std::mutex> l(g_prof.mu);
+    g_prof.pending.push_back(p);
+}
+void nlzm_launch_end(cudaStream_t st) {
+    if (!g_prof.on) return;
+    std::lock_guard<std::mutex> l(g_prof.mu);
+    cudaEventRecord(g_prof.pending.back().b, st);
+}
+
+static std::string g_create_error;
+
+#define CK(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess) return fail((int)e_, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+#define CKI(expr)                                                                                  \
+    do {                                                                                           \
+        int r_ = (expr);                                                                           \
+        if (r_ != 0) return r_ < 0 ? r_ : fail(r_, std::string(#expr) + ": " + cudaGetErrorString((cudaError_t)r_)); \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    template <class T> T *as() const { return (T *)p; }
+};
+
+struct Slot {
+    DevBuf d_offsets, d_steps;
+    void *h_offsets = nullptr, *h_steps = nullptr;
+    size_t h_offsets_bytes = 0, h_steps_bytes = 0;
+    u64 begin = 0, end = 0, n_steps = 0;
+    std::thread worker;
+    bool pending = false;
+    int status = 0;
+};
+
+struct nlzm_mf {
+    Geom g;
+    int device = 0;
+    u32 mask = NLZM_MF_ALL;
+    u64 max_range = 0;
+    cudaStream_t st = 0;
+    DevBuf x;
+    bool have_input = false;
+
+    DevBuf k64[2], v32[2], rank, ptr, best, aux0, aux1;            // stages S/T
+    DevBuf tk[2], tv[2], tcount, keep, out_idx;                    // tuples / merge
+    DevBuf e_k[2], e_v[2], e_inv;                                  // HT / BT-short event sorts
+    DevBuf hblk, sl_k[2], sl_v[2], sl_cnt, sl_off;                 // RK table
+    DevBuf hit_k[2], hit_v[2], hit_len, hit_count, iv, n_iv;       // RK hits / carry intervals
+    DevBuf scalars;                                                // misc device scalars
+    PrimTemp tmp;
+    DevBuf tmpbuf;
+    u32 tuple_cap_mult = 6;
+
+    Slot slot[2];
+    std::mutex mu;
+    std::string err;
+    nlzm_mf_stats stats{};
+
+    int fail(int code, const std::string &msg) {
+        err = msg;
+        return code;
+    }
+
+    int ensure(DevBuf &b, size_t bytes) {
+        if (bytes <= b.bytes) return 0;
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.bytes = 0;
+        size_t want = bytes + (bytes >> 4) + 256;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) {
+            b.p = nullptr;
+            return fail(NLZM_MF_E_NOMEM, "cudaMalloc(" + std::to_string(want) + "): " + cudaGetErrorString(e));
+        }
+        b.bytes = want;
+        return 0;
+    }
+    void release(DevBuf &b) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+
+    int ensure_prim(u64 n) {
+        size_t need = prim_temp_bytes(n);
+        int r = ensure(tmpbuf, need);
+        if (r) return r;
+        tmp.ptr = tmpbuf.p;
+        tmp.bytes = tmpbuf.bytes;
+        return 0;
+    }
+
+    TupleSink sink() {
+        TupleSink s;
+        s.keys = tk[0].as<u64>();
+        s.vals = tv[0].as<u32>();
+        s.count = tcount.as<u32>();
+        s.cap = (u32)(tk[0].bytes / 8 < tv[0].bytes / 4 ? tk[0].bytes / 8 : tv[0].bytes / 4);
+        return s;
+    }
+
+    int stage_bt4(u64 own_b, u64 own_e);
+    int stage_ht(u64 own_b, u64 own_e, const HtCfg &c);
+    int stage_rk(u64 own_b, u64 own_e);
+    int stage_merge(u64 own_b, u64 own_e, Slot &s);
+    int find_impl(u64 b, u64 e, int slot, bool to_host);
+};
+
+static inline u32 bits_for(u64 v) {
+    u32 b = 0;
+    while ((1ull << b) < v) ++b;
+    return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage S + T (+ the 2..3-byte bucket-collision candidates of small windows)
+// ------------------------------------------------------------------------------------------------
+int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
+    const u64 u0 = own_b > (u64)(g.W - 1) ? own_b - (g.W - 1) : 0;
+    const u64 u1 = own_e + 1024 < g.flen ? own_e + 1024 : g.flen;
+    const u64 n = u1 - u0;
+    if (n < 2) return 0;
+    CKI(ensure(k64[0], n * 8)); CKI(ensure(k64[1], n * 8));
+    CKI(ensure(v32[0], n * 4)); CKI(ensure(v32[1], n * 4));
+    CKI(ensure(rank, n * 4)); CKI(ensure(aux0, n * 4)); CKI(ensure(aux1, n * 4));
+    CKI(ensure(ptr, n * sizeof(PtrEntry))); CKI(ensure(best, n * 2));
+    CKI(ensure_prim(n));
+    u64 *sum_dev = scalars.as<u64>();
+
+    cudaEvent_t ev0, ev1, ev2;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&ev2);
+    cudaEventRecord(ev0, st);
+
+    // --- S: prefix doubling 8 -> 16 -> ... -> >= 264 bytes
+    RankInitParams ip{x.as<u8>(), u0, k64[0].as<u64>(), v32[0].as<u32>()};
+    launch_rank_init(ip, n, st);
+    u64 depth = 8;
+    while (true) {
+        int sel = 0;
+        CKI(prim_sort_pairs64(tmp, k64[0].as<u64>(), k64[1].as<u64>(), v32[0].as<u32>(), v32[1].as<u32>(), n, 0, 64, st, &sel));
+        RankHeadParams hp{k64[sel].as<u64>(), aux0.as<u32>(), aux1.as<u32>()};
+        launch_rank_head(hp, n, st);
+        CKI(prim_sum(tmp, aux1.as<u32>(), sum_dev, n, st));
+        CKI(prim_inclusive_max(tmp, aux0.as<u32>(), aux0.as<u32>(), n, st));
+        RankScatterParams sp{v32[sel].as<u32>(), aux0.as<u32>(), rank.as<u32>()};
+        launch_rank_scatter(sp, n, st);
+        u64 groups = 0;
+        CK(cudaMemcpyAsync(&groups, sum_dev, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (depth >= NLZM_MATCH_MAX || groups == n) break;
+        RankPairParams pp{rank.as<u32>(), k64[0].as<u64>(), v32[0].as<u32>(), n, depth};
+        launch_rank_pair(pp, n, st);
+        depth *= 2;
+    }
+    RankElemParams ep{rank.as<u32>(), k64[0].as<u64>()};
+    launch_rank_elem(ep, n, st);
+    cudaEventRecord(ev1, st);
+
+    // --- T: levels
+    DcInitParams dp{ptr.as<PtrEntry>(), best.as<u16>(), (u16)3};
+    launch_dc_init(dp, n, st);
+    LevelParams lp;
+    lp.corank = rank.as<u32>();          // ranks now live inside the element keys
+    lp.ptr = ptr.as<PtrEntry>();
+    lp.best = best.as<u16>();
+    lp.x = x.as<u8>();
+    lp.g = g;
+    lp.u0 = u0;
+    lp.own_b = own_b;
+    lp.own_e = own_e;
+    lp.n = (u32)n;
+    lp.sink = sink();
+    int cur = 0;
+    for (u64 h = 1; h < n; h <<= 1) {
+        lp.cur = k64[cur].as<u64>();
+        lp.nxt = k64[cur ^ 1].as<u64>();
+        lp.h = (u32)h;
+        launch_dc_merge_query(lp, n, st);
+        launch_dc_link(lp, n, st);
+        cur ^= 1;
+    }
+
+    // --- lengths 2..3 inside a bucket (only windows < 2^19)
+    if (g.bt_bits < 16) {
+        const u64 pe = own_e < g.flen - 3 ? own_e : g.flen - 3;      // callers guarantee flen >= 4 here
+        if (pe > own_b) {
+            const u64 s0 = own_b > 4095 ? own_b - 4095 : 0;
+            const u64 m = pe - s0;
+            CKI(ensure(e_k[0], m * 4)); CKI(ensure(e_k[1], m * 4));
+            CKI(ensure(e_v[0], m * 4)); CKI(ensure(e_v[1], m * 4));
+            CKI(ensure(e_inv, m * 4));
+            CKI(ensure_prim(m));
+            BtBucketParams bp{x.as<u8>(), s0, 32 - g.bt_bits, e_k[0].as<u32>(), e_v[0].as<u32>()};
+            launch_bt_bucket(bp, m, st);
+            int sel = 0;
+            CKI(prim_sort_pairs32(tmp, e_k[0].as<u32>(), e_k[1].as<u32>(), e_v[0].as<u32>(), e_v[1].as<u32>(), m, 0, (int)g.bt_bits, st, &sel));
+            HtInvParams vp{e_v[sel].as<u32>(), e_inv.as<u32>()};
+            launch_ht_inv(vp, m, st);
+            BtShortParams sp{x.as<u8>(), g, e_k[sel].as<u32>(), e_v[sel].as<u32>(), e_inv.as<u32>(), s0, own_b, sink()};
+            launch_bt_short(sp, pe - own_b, st);
+        }
+    }
+    cudaEventRecord(ev2, st);
+    CK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&stats.ms_rank, ev0, ev1);
+    cudaEventElapsedTime(&stats.ms_levels, ev1, ev2);
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage H
+// ------------------------------------------------------------------------------------------------
+int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
+    if (g.flen < 4) return 0;
+    const u64 pe = own_e < g.flen - 3 ? own_e : g.flen - 3;          // accesses happen while 4 bytes are visible
+    if (pe <= own_b) return 0;
+    const u64 m = pe * c.rows;                                       // events of the whole prefix (tables never age)
+    CKI(ensure(e_k[0], m * 4)); CKI(ensure(e_k[1], m * 4));
+    CKI(ensure(e_v[0], m * 4)); CKI(ensure(e_v[1], m * 4));
+    CKI(ensure(e_inv, m * 4));
+    CKI(ensure_prim(m));
+    HtEventParams ep{x.as<u8>(), c, e_k[0].as<u32>(), e_v[0].as<u32>()};
+    launch_ht_event(ep, pe, st);
+    int sel = 0;
+    CKI(prim_sort_pairs32(tmp, e_k[0].as<u32>(), e_k[1].as<u32>(), e_v[0].as<u32>(), e_v[1].as<u32>(), m, 0, (int)c.bits + 1, st, &sel));
+    HtInvParams vp{e_v[sel].as<u32>(), e_inv.as<u32>()};
+    launch_ht_inv(vp, m, st);
+    HtFindParams fp{x.as<u8>(), g, c, e_k[sel].as<u32>(), e_v[sel].as<u32>(), e_inv.as<u32>(), own_b, sink()};
+    launch_ht_find(fp, pe - own_b, st);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage R
+// ------------------------------------------------------------------------------------------------
+int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
+    if (g.flen < NLZM_RK_BLOCK) return 0;
+    const u64 rk_e = own_e < g.flen - 255 ? own_e : g.flen - 255;    // RK is called while 256 bytes are visible
+    if (rk_e <= own_b) return 0;
+    // the carry state machine restarts cleanly at a ring shift: begin at the last one at or before own_b
+    u64 rk_b = 0;
+    const u32 ep = geom_epoch(g, own_b);
+    if (ep > 0) {
+        u64 k = (((u64)(ep + 1) << g.hb) + g.cs - 1) / g.cs;
+        rk_b = k * g.cs;
+    }
+    const u64 n_blk = (rk_e + NLZM_RK_BLOCK - 1) / NLZM_RK_BLOCK;    // blocks starting before rk_e (each has 256 bytes)
+    const u64 n_slots = 1ull << g.rk_bits;
+    CKI(ensure(hblk, n_blk * 4));
+    CKI(ensure(sl_k[0], n_blk * 4)); CKI(ensure(sl_k[1], n_blk * 4));
+    CKI(ensure(sl_v[0], n_blk * 4)); CKI(ensure(sl_v[1], n_blk * 4));
+    CKI(ensure(sl_cnt, (n_slots + 1) * 4)); CKI(ensure(sl_off, (n_slots + 1) * 4));
+    const u64 range = rk_e - rk_b;
+    u64 hit_cap = range / 4 + (1u << 20);
+    CKI(ensure(hit_k[0], hit_cap * 8)); CKI(ensure(hit_k[1], hit_cap * 8));
+    CKI(ensure(hit_v[0], hit_cap * 4)); CKI(ensure(hit_v[1], hit_cap * 4));
+    CKI(ensure(hit_len, hit_cap * 4));
+    CKI(ensure(iv, hit_cap * sizeof(RkInterval)));
+    CKI(ensure_prim(n_blk > n_slots + 1 ? n_blk : n_slots + 1));
+    CKI(ensure_prim(hit_cap));
+    u32 *hit_count = scalars.as<u32>() + 8;
+    u32 *n_iv = scalars.as<u32>() + 9;
+
+    CK(cudaMemsetAsync(sl_cnt.p, 0, (n_slots + 1) * 4, st));
+    CK(cudaMemsetAsync(hit_count, 0, 8, st));
+    RkBlockParams bp{x.as<u8>(), hblk.as<u32>(), sl_k[0].as<u32>(), sl_v[0].as<u32>(), sl_cnt.as<u32>(), 32 - g.rk_bits};
+    launch_rk_block(bp, n_blk, st);
+    int sel = 0;
+    CKI(prim_sort_pairs32(tmp, sl_k[0].as<u32>(), sl_k[1].as<u32>(), sl_v[0].as<u32>(), sl_v[1].as<u32>(), n_blk, 0, (int)g.rk_bits, st, &sel));
+    CKI(prim_exclusive_sum(tmp, sl_cnt.as<u32>(), sl_off.as<u32>(), n_slots + 1, st));
+
+    RkLookupParams lp;
+    lp.x = x.as<u8>(); lp.g = g; lp.hblk = hblk.as<u32>(); lp.slot_off = sl_off.as<u32>(); lp.slot_blk = sl_v[sel].as<u32>();
+    lp.rk_b = rk_b; lp.rk_e = rk_e; lp.span = 64;
+    lp.hit_keys = hit_k[0].as<u64>(); lp.hit_vals = hit_v[0].as<u32>(); lp.hit_count = hit_count; lp.hit_cap = (u32)hit_cap;
+    launch_rk_lookup(lp, (range + lp.span - 1) / lp.span, st);
+    u32 n_hits = 0;
+    CK(cudaMemcpyAsync(&n_hits, hit_count, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (n_hits > hit_cap) return fail(NLZM_MF_E_OVERFLOW, "RK raw-hit buffer overflow");
+    if (n_hits == 0) return 0;
+    int hsel = 0;
+    CKI(prim_sort_pairs64(tmp, hit_k[0].as<u64>(), hit_k[1].as<u64>(), hit_v[0].as<u32>(), hit_v[1].as<u32>(), n_hits, 0, (int)bits_for(g.flen + 1), st, &hsel));
+    RkExtendParams xp{x.as<u8>(), g, hit_k[hsel].as<u64>(), hit_v[hsel].as<u32>(), hit_len.as<u32>()};
+    launch_rk_extend(xp, n_hits, st);
+    RkChainParams cp{g, hit_k[hsel].as<u64>(), hit_v[hsel].as<u32>(), hit_len.as<u32>(), hit_count, iv.as<RkInterval>(), n_iv};
+    launch_rk_chain(cp, 1, st);
+    u32 niv = 0;
+    CK(cudaMemcpyAsync(&niv, n_iv, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    RkExpandParams ex{g, iv.as<RkInterval>(), own_b, own_e, sink()};
+    launch_rk_expand(ex, niv, st);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage M
+// ------------------------------------------------------------------------------------------------
+int nlzm_mf::stage_merge(u64 own_b, u64 own_e, Slot &s) {
+    const u64 n_own = own_e - own_b;
+    u32 nt = 0;
+    CK(cudaMemcpyAsync(&nt, tcount.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    stats.tuples_last = nt;
+    const u32 cap = sink().cap;
+    if (nt > cap) return fail(NLZM_MF_E_OVERFLOW, "candidate tuple buffer overflow");
+    CKI(ensure(s.d_offsets, (n_own + 1) * 4));
+    CK(cudaMemsetAsync(s.d_offsets.p, 0, (n_own + 1) * 4, st));
+    s.n_steps = 0;
+    if (nt == 0) return 0;
+    CKI(ensure(keep, (u64)nt * 4)); CKI(ensure(out_idx, (u64)nt * 4));
+    CKI(ensure(aux0, (n_own + 1) * 4));
+    CKI(ensure_prim(nt > n_own + 1 ? nt : n_own + 1));
+    int sel = 0;
+    CKI(prim_sort_pairs64(tmp, tk[0].as<u64>(), tk[1].as<u64>(), tv[0].as<u32>(), tv[1].as<u32>(), nt, 0, (int)(9 + bits_for(n_own + 1)), st, &sel));
+    u32 *count = aux0.as<u32>();
+    CK(cudaMemsetAsync(count, 0, (n_own + 1) * 4, st));
+    FilterParams fp{tk[sel].as<u64>(), tv[sel].as<u32>(), nt, keep.as<u32>(), count};
+    launch_step_filter(fp, nt, st);
+    CKI(prim_exclusive_sum(tmp, count, s.d_offsets.as<u32>(), n_own + 1, st));
+    CKI(prim_exclusive_sum(tmp, keep.as<u32>(), out_idx.as<u32>(), nt, st));
+    u32 total = 0;
+    CK(cudaMemcpyAsync(&total, s.d_offsets.as<u32>() + n_own, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    s.n_steps = total;
+    CKI(ensure(s.d_steps, (u64)(total ? total : 1) * sizeof(Step)));
+    CompactParams cp{tk[sel].as<u64>(), tv[sel].as<u32>(), keep.as<u32>(), out_idx.as<u32>(), s.d_steps.as<Step>()};
+    launch_step_compact(cp, nt, st);
+    return 0;
+}
+
+int nlzm_mf::find_impl(u64 b, u64 e, int si, bool to_host) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!have_input) return fail(NLZM_MF_E_STATE, "find before set_input");
+    if (si < 0 || si > 1) return fail(NLZM_MF_E_ARG, "slot must be 0 or 1");
+    if (b > e || e > g.flen) return fail(NLZM_MF_E_ARG, "bad range");
+    if (e - b > (1ull << 28)) return fail(NLZM_MF_E_ARG, "range larger than 2^28 positions: split it");
+#ifndef NLZM_EMU
+    CK(cudaSetDevice(device));
+#endif
+    Slot &s = slot[si];
+    s.begin = b; s.end = e; s.n_steps = 0;
+    const u64 n_own = e - b;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        const u64 cap = n_own * tuple_cap_mult + (1u << 20);
+        if (cap >= 0xFFFFFFF0ull) return fail(NLZM_MF_E_OVERFLOW, "candidate tuple capacity exceeds 2^32");
+        CKI(ensure(tk[0], cap * 8)); CKI(ensure(tk[1], cap * 8));
+        CKI(ensure(tv[0], cap * 4)); CKI(ensure(tv[1], cap * 4));
+        CK(cudaMemsetAsync(tcount.p, 0, 4, st));
+        cudaEvent_t e0, e1, e2, e3, e4;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3); cudaEventCreate(&e4);
+        cudaEventRecord(e0, st);
+        stats.ms_rank = stats.ms_levels = 0;
+        int r = 0;
+        if (n_own > 0) {
+            if (r == 0 && (mask & NLZM_MF_BT4) && g.flen >= 4) r = stage_bt4(b, e);
+            cudaEventRecord(e1, st);
+            if (r == 0 && (mask & NLZM_MF_HT2)) { HtCfg c{1, 12, 2}; r = stage_ht(b, e, c); }
+            if (r == 0 && (mask & NLZM_MF_HT3)) { HtCfg c{2, g.ht3_bits, 3}; r = stage_ht(b, e, c); }
+            cudaEventRecord(e2, st);
+            if (r == 0 && (mask & NLZM_MF_RK256)) r = stage_rk(b, e);
+            cudaEventRecord(e3, st);
+        } else {
+            cudaEventRecord(e1, st); cudaEventRecord(e2, st); cudaEventRecord(e3, st);
+        }
+        if (r == 0) r = stage_merge(b, e, s);
+        cudaEventRecord(e4, st);
+        cudaStreamSynchronize(st);
+        if (r == 0) {
+            cudaEventElapsedTime(&stats.ms_ht, e1, e2);
+            cudaEventElapsedTime(&stats.ms_rk, e2, e3);
+            cudaEventElapsedTime(&stats.ms_merge, e3, e4);
+            cudaEventElapsedTime(&stats.ms_total, e0, e4);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); cudaEventDestroy(e4);
+        if (r == NLZM_MF_E_OVERFLOW && attempt < 3) {      // rare: dense candidates; grow and redo the range
+            tuple_cap_mult *= 2;
+            continue;
+        }
+        if (r) return r;
+        break;
+    }
+    stats.kernel_launches = g_launches.load();
+    stats.ms_d2h = 0;
+    if (g_prof.on) g_prof.resolve();
+    if (to_host) {
+        size_t ob = (n_own + 1) * 4, sb = (size_t)(s.n_steps ? s.n_steps : 1) * sizeof(Step);
+        if (ob > s.h_offsets_bytes) {
+            if (s.h_offsets) cudaFreeHost(s.h_offsets);
+            s.h_offsets = nullptr; s.h_offsets_bytes = 0;
+            CK(cudaMallocHost(&s.h_offsets, ob + (ob >> 3)));
+            s.h_offsets_bytes = ob + (ob >> 3);
+        }
+        if (sb > s.h_steps_bytes) {
+            if (s.h_steps) cudaFreeHost(s.h_steps);
+            s.h_steps = nullptr; s.h_steps_bytes = 0;
+            CK(cudaMallocHost(&s.h_steps, sb + (sb >> 3)));
+            s.h_steps_bytes = sb + (sb >> 3);
+        }
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, st);
+        CK(cudaMemcpyAsync(s.h_offsets, s.d_offsets.p, ob, cudaMemcpyDeviceToHost, st));
+        if (s.n_steps) CK(cudaMemcpyAsync(s.h_steps, s.d_steps.p, s.n_steps * sizeof(Step), cudaMemcpyDeviceToHost, st));
+        cudaEventRecord(e1, st);
+        CK(cudaStreamSynchronize(st));
+        cudaEventElapsedTime(&stats.ms_d2h, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int nlzm_mf_abi_version(void) { return NLZM_MF_ABI_VERSION; }
+
+int nlzm_mf_get_geometry(uint64_t file_len, uint32_t hist_bits, nlzm_mf_geometry *out) {
+    if (!out) return NLZM_MF_E_ARG;
+    Geom g = make_geom(file_len, hist_bits);
+    out->hist_bits = g.hb;
+    out->window = g.W;
+    out->frame_bits = nlzm_clampu(g.hb - 2, 14, 17);
+    out->chunk_size = g.cs;
+    out->feed_size = g.cs + NLZM_MATCH_MAX + 1;
+    out->ht2_bits = 12;
+    out->ht3_bits = g.ht3_bits;
+    out->bt4_bits = g.bt_bits;
+    out->rk_bits = g.rk_bits;
+    return 0;
+}
+
+int nlzm_mf_create(const nlzm_mf_config *cfg, nlzm_mf **out) {
+    if (!cfg || !out || cfg->struct_size != sizeof(nlzm_mf_config)) { g_create_error = "bad config"; return NLZM_MF_E_ARG; }
+    if (cfg->file_len >= (1ull << 31)) { g_create_error = "file_len must be < 2^31"; return NLZM_MF_E_ARG; }
+    *out = nullptr;
+#ifndef NLZM_EMU
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (") + cudaGetErrorString(e) + "); this engine has no CPU fallback";
+        return NLZM_MF_E_NODEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return NLZM_MF_E_ARG; }
+    cudaSetDevice(cfg->device);
+#endif
+    nlzm_mf *mf = new nlzm_mf();
+    mf->g = make_geom(cfg->file_len, cfg->hist_bits);
+    mf->device = cfg->device;
+    mf->mask = cfg->finder_mask ? cfg->finder_mask : (u32)NLZM_MF_ALL;
+    mf->max_range = cfg->max_range ? cfg->max_range : cfg->file_len;
+#ifndef NLZM_EMU
+    if (cudaStreamCreateWithFlags(&mf->st, cudaStreamNonBlocking) != cudaSuccess) {
+        g_create_error = "cudaStreamCreate failed";
+        delete mf;
+        return NLZM_MF_E_NODEVICE;
+    }
+#endif
+    int r = mf->ensure(mf->x, cfg->file_len + NLZM_X_PAD + 8);
+    if (r == 0) r = mf->ensure(mf->tcount, 64);
+    if (r == 0) r = mf->ensure(mf->scalars, 256);
+    if (r) { g_create_error = mf->err; nlzm_mf_destroy(mf); return r; }
+    *out = mf;
+    return 0;
+}
+
+void nlzm_mf_destroy(nlzm_mf *mf) {
+    if (!mf) return;
+    for (auto &s : mf->slot) {
+        if (s.worker.joinable()) s.worker.join();
+        mf->release(s.d_offsets); mf->release(s.d_steps);
+        if (s.h_offsets) cudaFreeHost(s.h_offsets);
+        if (s.h_steps) cudaFreeHost(s.h_steps);
+    }
+    DevBuf *all[] = {&mf->x, &mf->k64[0], &mf->k64[1], &mf->v32[0], &mf->v32[1], &mf->rank, &mf->ptr, &mf->best, &mf->aux0,
+                     &mf->aux1, &mf->tk[0], &mf->tk[1], &mf->tv[0], &mf->tv[1], &mf->tcount, &mf->keep, &mf->out_idx,
+                     &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
+                     &mf->sl_v[0], &mf->sl_v[1], &mf->sl_cnt, &mf->sl_off, &mf->hit_k[0], &mf->hit_k[1], &mf->hit_v[0],
+                     &mf->hit_v[1], &mf->hit_len, &mf->hit_count, &mf->iv, &mf->n_iv, &mf->scalars, &mf->tmpbuf};
+    for (DevBuf *b : all) mf->release(*b);
+#ifndef NLZM_EMU
+    if (mf->st) cudaStreamDestroy(mf->st);
+#endif
+    delete mf;
+}
+
+const char *nlzm_mf_last_error(const nlzm_mf *mf) { return mf ? mf->err.c_str() : g_create_error.c_str(); }
+
+static int set_input_common(nlzm_mf *mf, const void *src, uint64_t len, bool from_device) {
+    if (!mf || (!src && len)) return NLZM_MF_E_ARG;
+    if (len != mf->g.flen) return mf->fail(NLZM_MF_E_ARG, "set_input length differs from config.file_len");
+    std::lock_guard<std::mutex> lock(mf->mu);
+#ifndef NLZM_EMU
+    cudaSetDevice(mf->device);
+#endif
+    cudaError_t e = cudaMemsetAsync((u8 *)mf->x.p + len, 0, NLZM_X_PAD + 8, mf->st);
+    if (e == cudaSuccess && len)
+        e = cudaMemcpyAsync(mf->x.p, src, len, from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, mf->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
+    if (e != cudaSuccess) return mf->fail((int)e, std::string("set_input: ") + cudaGetErrorString(e));
+    mf->have_input = true;
+    return 0;
+}
+
+int nlzm_mf_set_input(nlzm_mf *mf, const uint8_t *host_data, uint64_t len) { return set_input_common(mf, host_data, len, false); }
+int nlzm_mf_set_input_device(nlzm_mf *mf, const void *device_data, uint64_t len) { return set_input_common(mf, device_data, len, true); }
+
+static void fill_view(nlzm_mf *mf, int slot, bool host, nlzm_mf_view *out) {
+    Slot &s = mf->slot[slot];
+    out->begin = s.begin;
+    out->end = s.end;
+    out->n_steps = s.n_steps;
+    out->offsets = host ? (const uint32_t *)s.h_offsets : s.d_offsets.as<uint32_t>();
+    out->steps = host ? (const nlzm_mf_step *)s.h_steps : (const nlzm_mf_step *)s.d_steps.p;
+}
+
+int nlzm_mf_find(nlzm_mf *mf, uint64_t begin, uint64_t end, int slot, nlzm_mf_view *out) {
+    if (!mf || !out) return NLZM_MF_E_ARG;
+    int r = mf->find_impl(begin, end, slot, true);
+    if (r == 0) fill_view(mf, slot, true, out);
+    return r;
+}
+
+int nlzm_mf_find_device(nlzm_mf *mf, uint64_t begin, uint64_t end, int slot, nlzm_mf_view *out) {
+    if (!mf || !out) return NLZM_MF_E_ARG;
+    int r = mf->find_impl(begin, end, slot, false);
+    if (r == 0) fill_view(mf, slot, false, out);
+    return r;
+}
+
+int nlzm_mf_submit(nlzm_mf *mf, uint64_t begin, uint64_t end, int slot) {
+    if (!mf || slot < 0 || slot > 1) return NLZM_MF_E_ARG;
+    Slot &s = mf->slot[slot];
+    if (s.pending) return mf->fail(NLZM_MF_E_STATE, "slot already has a pending submit");
+    if (s.worker.joinable()) s.worker.join();
+    s.pending = true;
+    s.worker = std::thread([mf, begin, end, slot]() { mf->slot[slot].status = mf->find_impl(begin, end, slot, true); });
+    return 0;
+}
+
+int nlzm_mf_fetch(nlzm_mf *mf, int slot, nlzm_mf_view *out) {
+    if (!mf || !out || slot < 0 || slot > 1) return NLZM_MF_E_ARG;
+    Slot &s = mf->slot[slot];
+    if (!s.pending) return mf->fail(NLZM_MF_E_STATE, "fetch without submit");
+    s.worker.join();
+    s.pending = false;
+    if (s.status == 0) fill_view(mf, slot, true, out);
+    return s.status;
+}
+
+int nlzm_mf_profile(int enable) {
+    g_prof.on = enable != 0;
+    if (!enable) {
+        std::lock_guard<std::mutex> l(g_prof.mu);
+        g_prof.acc.clear();
+    }
+    return 0;
+}
+
+int nlzm_mf_get_kernel_times(nlzm_mf_kernel_time *out, uint32_t cap, uint32_t *n_out) {
+    if (!n_out) return NLZM_MF_E_ARG;
+    std::lock_guard<std::mutex> l(g_prof.mu);
+    uint32_t i = 0;
+    for (auto &kv : g_prof.acc) {
+        if (out && i < cap) {
+            memset(&out[i], 0, sizeof out[i]);
+            strncpy(out[i].name, kv.first.c_str(), sizeof(out[i].name) - 1);
+            out[i].launches = kv.second.first;
+            out[i].ms = kv.second.second;
+        }
+        ++i;
+    }
+    *n_out = i;
+    return 0;
+}
+
+int nlzm_mf_get_stats(const nlzm_mf *mf, nlzm_mf_stats *out) {
+    if (!mf || !out) return NLZM_MF_E_ARG;
+    *out = mf->stats;
+    out->kernel_launches = g_launches.load();
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,73 @@
+// Build-mode glue. The product is compiled by nvcc for sm_100a. The same kernel bodies can also
+// be compiled by g++ with -DNLZM_EMU into a *test-only* library (tests/emu) in which every
+// "kernel" is a sequential loop over its thread index: that library exists so that the kernel
+// logic can be unit-tested in a container without a GPU. It is never shipped or loaded by the
+// nlzm_b200 package (nlzm_b200/_lib.py loads libnlzm_mf.so only and fails loudly without CUDA).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int64_t i64;
+
+#ifndef NLZM_EMU
+#include <cuda_runtime.h>
+#define HD __host__ __device__ __forceinline__
+#define DEV __device__ __forceinline__
+
+// One thread per element i < n; the kernel is named k_<name> so that ncu shows a readable symbol.
+#define NLZM_KERNEL_1D(name, ParamsT)                                                   \
+    __global__ void __launch_bounds__(256) k_##name(const ParamsT p, u64 n) {           \
+        u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;                             \
+        if (i < n) name##_body(p, i);                                                   \
+    }                                                                                   \
+    static inline void launch_##name(const ParamsT &p, u64 n, cudaStream_t st) {        \
+        if (n == 0) return;                                                             \
+        nlzm_launch_begin("k_" #name, st);                                              \
+        k_##name<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n);                    \
+        nlzm_launch_end(st);                                                            \
+    }
+DEV u32 nlzm_atomic_add(u32 *p, u32 v) { return atomicAdd(p, v); }
+DEV u64 nlzm_atomic_add64(unsigned long long *p, u64 v) { return atomicAdd(p, (unsigned long long)v); }
+DEV u32 nlzm_atomic_max(u32 *p, u32 v) { return atomicMax(p, v); }
+HD int nlzm_ctz64(u64 v) {
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+#else
+// ---- emulation (tests only) ----
+#include <stdlib.h>
+#include <stdio.h>
+#define HD inline
+#define DEV inline
+#define __global__
+#define __device__
+#define __host__
+#define __restrict__
+#define __forceinline__
+typedef int cudaStream_t;
+typedef int cudaError_t;
+#define cudaSuccess 0
+#define NLZM_KERNEL_1D(name, ParamsT)                                                   \
+    static inline void launch_##name(const ParamsT &p, u64 n, cudaStream_t st) {        \
+        nlzm_launch_begin("k_" #name, st);                                              \
+        for (u64 i = 0; i < n; i++) name##_body(p, i);                                  \
+        nlzm_launch_end(st);                                                            \
+    }
+static inline u32 nlzm_atomic_add(u32 *p, u32 v) { u32 o = *p; *p += v; return o; }
+static inline u64 nlzm_atomic_add64(unsigned long long *p, u64 v) { u64 o = *p; *p += v; return o; }
+static inline u32 nlzm_atomic_max(u32 *p, u32 v) { u32 o = *p; if (v > o) *p = v; return o; }
+static inline int nlzm_ctz64(u64 v) { return __builtin_ctzll(v); }
+#endif
+
+// launch accounting (engine.cu): every kernel launch is counted; with profiling on, it is also
+// bracketed by CUDA events on its stream and its time accumulated per kernel name.
+void nlzm_launch_begin(const char *name, cudaStream_t st);
+void nlzm_launch_end(cudaStream_t st);

@@ -1,0 +1,158 @@
+// Stage R — RK256 long-range finder (NLZM.cpp:1033-1123) in order-independent form.
+//
+//  1. hash of every 256-aligned block  H(s) = sum x[s+i] * ADDH^(256-i)  (NLZM.cpp:798-799)
+//  2. "table build": blocks radix-sorted by slot (stable => time order) + CSR offsets; the one-entry
+//     table of the reference holds, at time a, the last block of the slot that starts before a
+//  3. per position: rolling hash, slot lookup, check bits / window test exactly as written
+//     (entries keep the full shifted position, so bits >= hist_bits leak into the check field;
+//     an empty slot is the raw word 0xFFFFFFFF and is matched like any entry) -> raw hit list
+//  4. extension of every raw hit to its full length (cap = uint16(remaining), NLZM.cpp:759-760,1096)
+//  5. the carried-match state machine over the sparse, position-sorted hit list (NLZM.cpp:1056-1069,
+//     1090-1107): which hits are looked up at all, which are accepted, how long each carry lives
+//  6. expansion of the carry intervals into per-position candidates
+#pragma once
+#include "common.cuh"
+#include "dc_levels.cuh"
+
+HD u32 rk_hash_block(const u8 *__restrict__ x, u64 s) {
+    u32 h = 0;
+    for (u32 i = 0; i < NLZM_RK_BLOCK; i += 8) {
+        u64 w = load8(x, s + i);
+        #pragma unroll
+        for (int b = 0; b < 8; b++) h = ((u32)((w >> (8 * b)) & 0xFF) + h) * NLZM_RK_ADDH;   // rolling_hash_add
+    }
+    return h;
+}
+
+struct RkBlockParams { const u8 *x; u32 *hblk; u32 *slot_keys; u32 *vals; u32 *slot_count; u32 shift; };
+DEV void rk_block_body(const RkBlockParams &p, u64 j) {
+    u32 h = rk_hash_block(p.x, j * NLZM_RK_BLOCK);
+    p.hblk[j] = h;
+    p.slot_keys[j] = h >> p.shift;
+    p.vals[j] = (u32)j;
+    nlzm_atomic_add(p.slot_count + (h >> p.shift), 1u);
+}
+NLZM_KERNEL_1D(rk_block, RkBlockParams)
+
+struct RkLookupParams {
+    const u8 *x;
+    Geom g;
+    const u32 *hblk;        // hash per aligned block
+    const u32 *slot_off;    // CSR offsets per slot (2^rk_bits + 1)
+    const u32 *slot_blk;    // block indices sorted by (slot, block)
+    u64 rk_b;               // first position looked up
+    u64 rk_e;               // one past the last position looked up
+    u32 span;               // positions per thread
+    u64 *hit_keys;          // absolute position of the raw hit
+    u32 *hit_vals;          // its distance
+    u32 *hit_count;
+    u32 hit_cap;
+};
+
+// One thread rolls the hash over `span` consecutive positions (NLZM.cpp:799) and does the lookups.
+DEV void rk_lookup_body(const RkLookupParams &p, u64 t) {
+    u64 a = p.rk_b + t * p.span;
+    if (a >= p.rk_e) return;
+    u64 a_end = a + p.span < p.rk_e ? a + p.span : p.rk_e;
+    const u32 shift = 32 - p.g.rk_bits;
+    const u32 cmask = (1u << (32 - p.g.hb)) - 1;
+    u32 h = rk_hash_block(p.x, a);
+    for (;; ) {
+        const u32 slot = h >> shift;
+        // last block of this slot that starts before a (the insert at a itself comes after the lookup)
+        u32 lo = p.slot_off[slot], hi = p.slot_off[slot + 1];
+        u32 e = NLZM_NONE32;
+        while (hi > lo) {
+            u32 j = p.slot_blk[hi - 1];
+            if ((u64)j * NLZM_RK_BLOCK < a) {
+                u64 s = (u64)j * NLZM_RK_BLOCK;
+                e = geom_P(p.g, s) | (p.hblk[j] << p.g.hb);      // NLZM.cpp:1111: full P, spills into the check bits
+                break;
+            }
+            --hi;
+        }
+        const u32 P = geom_P(p.g, a);
+        const u32 sp = e & (p.g.W - 1);
+        if ((e >> p.g.hb) == (h & cmask) && sp < P && P - sp <= p.g.W - 1) {     // NLZM.cpp:1091-1095
+            u32 idx = nlzm_atomic_add(p.hit_count, 1u);
+            if (idx < p.hit_cap) { p.hit_keys[idx] = a; p.hit_vals[idx] = P - sp; }
+        }
+        if (++a >= a_end) break;
+        h = ((u32)p.x[a + NLZM_RK_BLOCK - 1] + h - (u32)p.x[a - 1] * NLZM_RK_REMH) * NLZM_RK_ADDH;   // rolling_hash_add_remove
+    }
+}
+NLZM_KERNEL_1D(rk_lookup, RkLookupParams)
+
+struct RkExtendParams { const u8 *x; Geom g; const u64 *hit_pos; const u32 *hit_dist; u32 *hit_len; };
+DEV void rk_extend_body(const RkExtendParams &p, u64 i) {
+    const u64 a = p.hit_pos[i];
+    const u32 d = p.hit_dist[i];
+    const u32 cap = geom_rem(p.g, a) & 0xFFFFu;          // uint16 max_len parameter, NLZM.cpp:759-760,1096-1097
+    p.hit_len[i] = lcp_cap(p.x, a - d, a, cap);
+}
+NLZM_KERNEL_1D(rk_extend, RkExtendParams)
+
+struct RkInterval { u64 start; u32 dist; u32 len; u64 end; };
+
+struct RkChainParams {
+    Geom g;
+    const u64 *hit_pos; const u32 *hit_dist; const u32 *hit_len;
+    const u32 *n_hits;
+    RkInterval *iv; u32 *n_iv;
+};
+
+HD u64 rk_carry_end(const Geom &g, u64 ca, u32 cl) {
+    // a carry dies when its length is used up or at the next ring shift (P - carry_to wraps, NLZM.cpp:1057)
+    u64 end = ca + cl;
+    const u32 ep = geom_epoch(g, ca);
+    // first chunk start after ca whose epoch differs: epochs only change at chunk starts
+    u64 k = ca / g.cs + 1;
+    // a carry spans at most 65535 positions => at most a few chunks
+    while (k * g.cs < end) {
+        if (geom_epoch(g, k * g.cs) != ep) { end = k * g.cs; break; }
+        ++k;
+    }
+    return end;
+}
+
+// The sequential part: one thread walks the position-sorted hits.
+DEV void rk_chain_body(const RkChainParams &p, u64) {
+    const u32 n = *p.n_hits;
+    u32 cl = 0, cd = 0, cep = 0, niv = 0;
+    u64 ca = 0;
+    for (u32 i = 0; i < n; i++) {
+        const u64 a = p.hit_pos[i];
+        const u32 d = p.hit_dist[i], m = p.hit_len[i];
+        if (m < match_min(d)) continue;                                   // not a hit at all (NLZM.cpp:1099)
+        const bool alive = cl > 0 && geom_epoch(p.g, a) == cep && a - ca < cl;
+        if (alive && cl >= NLZM_RK_BLOCK) continue;                       // no lookups under a long carry (1090)
+        if (alive && m < cl) continue;                                    // must be >= the carry's original length (1099)
+        if (cl > 0) {
+            u64 end = rk_carry_end(p.g, ca, cl);
+            RkInterval v; v.start = ca; v.dist = cd; v.len = cl; v.end = (a + 1 < end) ? a + 1 : end;   // (A) still fires at a
+            p.iv[niv++] = v;
+        }
+        ca = a; cd = d; cl = m; cep = geom_epoch(p.g, a);
+    }
+    if (cl > 0) {
+        RkInterval v; v.start = ca; v.dist = cd; v.len = cl; v.end = rk_carry_end(p.g, ca, cl);
+        p.iv[niv++] = v;
+    }
+    *p.n_iv = niv;
+}
+NLZM_KERNEL_1D(rk_chain, RkChainParams)
+
+struct RkExpandParams { Geom g; const RkInterval *iv; u64 own_b, own_e; TupleSink sink; };
+DEV void rk_expand_body(const RkExpandParams &p, u64 i) {
+    const RkInterval v = p.iv[i];
+    const u32 mm = match_min(v.dist);
+    u64 a = v.start > p.own_b ? v.start : p.own_b;
+    u64 end = v.end < p.own_e ? v.end : p.own_e;
+    for (; a < end; a++) {
+        if (p.g.flen - a < NLZM_RK_BLOCK) break;                      // RK is not called there (NLZM.cpp:1525)
+        u32 r = v.len - (u32)(a - v.start);
+        if (r < mm) break;                                            // only shrinks from here on
+        tuple_append(p.sink, (u32)(a - p.own_b), v.dist, r < NLZM_MATCH_MAX ? r : NLZM_MATCH_MAX);
+    }
+}
+NLZM_KERNEL_1D(rk_expand, RkExpandParams)
