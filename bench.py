@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — match-finding input MB/s of the B200 engine (and of the reference on the host CPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU)
+  python bench.py --impl reference [--gpus N] ...                reference arm (rank 0, host CPU)
+
+A step is one pass of the hot path — all four finders (HT2+HT3+BT4 exhaustive+RK256, "R2"
+semantics) over one batch of synthetic input:
+  N=1  BASELINE.json configs[1]: 100 MB enwik8-shaped text, -window:24 (C2)
+  N>1  weak scaling: the input is N x 100 MB, replicated in every GPU's HBM, rank r owns positions
+       [r*100 MB, (r+1)*100 MB) and builds its structures over its range plus the 16 MB window
+       behind it; no data-path collective. value = all positions / max-over-ranks time.
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PER_GPU_BYTES = 100_000_000
+HIST_BITS = 24
+CPU_SAMPLE = 1 << 23          # 8 MiB keeps -window:24 after the reference's shrink rule (flen >= 2^23)
+METRIC = "match-finding input MB/s"
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's own finder objects on the host CPU (oracle/_ref), else the C port
+# --------------------------------------------------------------------------------------------------
+
+def cpu_matcher_mbs(x_sample: np.ndarray, hist_bits: int):
+    """(MB/s, kind, description): reference match finding (HT2+HT3+BT4+RK256 with the shipped 256-test
+    cap, carry + skip rule as in parse_table, no pricing / coding) on one host thread."""
+    from oracle import refbind as rb
+    if rb.available():
+        _, secs = rb.matchfind(x_sample, hist_bits, mode=rb.R0, use_carry=True, dump_mask=0)
+        return x_sample.size / secs / 1e6, "reference", secs
+    from oracle import oracle as orc
+    t = time.perf_counter()
+    orc.find(x_sample, hist_bits, orc.F_ALL, 256)
+    secs = time.perf_counter() - t
+    return x_sample.size / secs / 1e6, "port", secs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from nlzm_b200 import synth
+    x = synth.text(CPU_SAMPLE, 1)           # same generator and seed as the GPU workload: its first 8 MiB
+    vals, kind = [], "reference"
+    for i in range(args.warmup + args.steps):
+        mbs, kind, secs = cpu_matcher_mbs(x, HIST_BITS)
+        if i >= args.warmup:
+            vals.append((mbs, secs))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([s for _, s in vals]) * 1e3)
+    sample = f"first {CPU_SAMPLE} bytes of the C2 text (seed 1), -window:{HIST_BITS}, one host thread (the reference has no threads)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"C2: 100 MB synthetic enwik8-shaped text, -window:{HIST_BITS}; each step = {sample}"},
+            "cpu_baseline": {"value": value, "unit": "MB/s", "cores": 1, "kind": kind, "sample": sample,
+                             "host_cores_available": os.cpu_count()},
+            "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nlzm_b200 import synth, sharding
+    from nlzm_b200.matchfinder import MatchFinders, profile, kernel_times, geometry
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    total = args.bytes_per_gpu * world
+    # input: generated once on rank 0, replicated into every GPU's HBM (setup, not the hot path)
+    if rank == 0:
+        x_host = synth.text(total, 1)
+        x_pin = torch.from_numpy(x_host).pin_memory()
+        x_dev = x_pin.to(dev, non_blocking=False)
+    else:
+        x_pin = None
+        x_dev = torch.empty(total, dtype=torch.uint8, device=dev)
+    if world > 1:
+        dist.broadcast(x_dev, src=0)
+        if rank != 0:
+            x_pin = x_dev.cpu().pin_memory()
+    torch.cuda.synchronize()
+
+    own_b, own_e = sharding.shard_range(total, rank, world)
+    n_own = own_e - own_b
+    blocks = sharding.split_blocks(own_b, own_e, args.block)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    mf = MatchFinders()
+    mf.Init(args.hist_bits, (x_dev.data_ptr(), total), device=local, max_range=args.block)
+    g = geometry(total, args.hist_bits)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        """one pass over this rank's positions, input resident in HBM, results left in HBM"""
+        ms, steps, tuples = 0.0, 0, 0
+        for i, (b, e) in enumerate(blocks):
+            v = mf.find_device(b, e, slot=i & 1)
+            s = mf.stats()
+            ms += s.ms_total
+            steps += int(v.n_steps)
+            tuples += int(s.tuples_last)
+        return ms, steps, tuples
+
+    def step_e2e():
+        """the call a user makes: host buffer in, host-visible candidates out (H2D + find + D2H)"""
+        t0 = time.perf_counter()
+        rc = mf._L.nlzm_mf_set_input(mf._h, C.c_void_p(x_pin.data_ptr()), total)
+        assert rc == 0
+        d2h = 0
+        for i, (b, e) in enumerate(blocks):
+            off, st = mf.FindAndUpdate(b, e, slot=i & 1, copy=False)
+            d2h += off.nbytes + st.nbytes
+        _ = int(off[-1])                     # device->host result is read on the host
+        return (time.perf_counter() - t0) * 1e3, d2h
+
+    # ---- warm-up (untimed): also sizes every buffer
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_resident()
+    step_e2e()
+
+    # ---- timed region: K resident steps, device time on the engine's stream, max over ranks
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    profile(True)
+    launches0 = int(mf.stats().kernel_launches)
+    t_wall0 = time.perf_counter()
+    dev_ms, n_steps, n_tuples = 0.0, 0, 0
+    for _ in range(args.steps):
+        flush.zero_()                        # L2 flush between timed iterations (256 MiB > 126 MB L2)
+        ms, n_steps, n_tuples = step_resident()
+        dev_ms += ms
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    launches = int(mf.stats().kernel_launches) - launches0
+    kt = kernel_times()
+    profile(False)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end-to-end: K steps with host buffers
+    barrier()
+    e2e_ms, d2h_bytes = 0.0, 0
+    for _ in range(args.steps):
+        ms, d2h_bytes = step_e2e()
+        e2e_ms += ms
+    barrier()
+
+    t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([n_steps, n_tuples, launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, wall_ms, e2e_ms = [float(v) for v in t.tolist()]
+    all_steps, all_tuples, all_launches = [int(v) for v in cnt.tolist()]
+
+    if rank == 0:
+        ms_per_step = dev_ms / args.steps
+        value = total / (ms_per_step * 1e-3) / 1e6
+        e2e_value = total / (e2e_ms / args.steps * 1e-3) / 1e6
+        # roofline of the dominant kernel (rank 0's launches). Algorithmic bytes, SURVEY.md §8(d):
+        #   short/medium stage  13*N + 8*steps,  RK256 stage  5.016*N (+12 per raw hit, negligible here)
+        # The dominant kernel is launched once per divide-and-conquer level; its L launches together do
+        # the short/medium stage for this rank's N positions, so one launch accounts for B_short / L.
+        peak, peak_src = measured_hbm_peak()
+        top = max(kt.items(), key=lambda kv: kv[1][1])
+        top_name, (top_launches, top_ms) = top
+        n_rank0 = n_own
+        b_short = 13.0 * n_rank0 + 8.0 * (all_steps / world)
+        per_launch_bytes = b_short / max(top_launches / args.steps, 1)
+        avg_launch_ms = top_ms / max(top_launches, 1)
+        achieved = per_launch_bytes / (avg_launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(top_name)
+        except Exception:
+            pass
+        roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": per_launch_bytes, "avg_launch_ms": avg_launch_ms,
+                    "launches_per_step": top_launches / args.steps,
+                    "whole_step": {"algorithmic_bytes": b_short + 5.016 * n_rank0,
+                                   "achieved": (b_short + 5.016 * n_rank0) / (ms_per_step * 1e-3) / 1e9,
+                                   "frac": (b_short + 5.016 * n_rank0) / (ms_per_step * 1e-3) / 1e9 / peak},
+                    "kernel_ms_per_step": {k: round(v[1] / args.steps, 3) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][1])}}
+        # CPU baseline: the reference's own matchers on one host core, bounded sample of the same workload
+        cpu_mbs, cpu_kind, cpu_secs = cpu_matcher_mbs(x_pin.numpy()[:CPU_SAMPLE], args.hist_bits)
+        line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"C2 x{world}: {total} B synthetic enwik8-shaped text (seed 1), -window:{args.hist_bits} "
+                                       f"(hist_bits {g.hist_bits}), finders HT2+HT3+BT4(exhaustive)+RK256, R2 semantics",
+                           "positions_per_gpu": n_own, "blocks_per_step": len(blocks),
+                           "sharding": "input replicated per GPU, position range sharded, no collective",
+                           "l2": "256 MiB flush buffer written between timed steps; working set ~5 GB >> 126 MB L2",
+                           "timing": "CUDA events on the engine's stream around every find; max over ranks",
+                           "staircase_steps": all_steps, "candidate_tuples": all_tuples},
+                "wall_ms_per_step": wall_ms / args.steps,
+                "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": total, "d2h_bytes_per_step": d2h_bytes,
+                        "ms_per_step": e2e_ms / args.steps,
+                        "path": "nlzm_mf_set_input(pinned host) + nlzm_mf_find (host view in pinned memory), wall clock"},
+                "gpu_launches": all_launches,
+                "roofline": roofline,
+                "cpu_baseline": {"value": cpu_mbs, "unit": "MB/s", "cores": 1, "kind": cpu_kind,
+                                 "sample": f"first {CPU_SAMPLE} bytes of the same text, -window:{args.hist_bits}, reference finders "
+                                           f"with the shipped 256-test cap + carry/skip rule, {cpu_secs:.1f} s",
+                                 "host_cores_available": os.cpu_count()},
+                "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    mf.Release()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bytes-per-gpu", type=int, default=PER_GPU_BYTES)
+    ap.add_argument("--hist-bits", type=int, default=HIST_BITS)
+    ap.add_argument("--block", type=int, default=1 << 27, help="positions per engine call")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,85 @@
+"""Kernel bodies + host orchestration of the engine, run sequentially on the CPU (tests/emu), against
+the oracle. This checks the logic that the GPU tests re-check on the real device."""
+import numpy as np
+import pytest
+
+from conftest import csr_from_find
+
+
+def _run(lib, x, hb, mask=15, cuts=None):
+    from nlzm_b200.matchfinder import MatchFinders
+    with MatchFinders(lib) as mf:
+        mf.Init(hb, x, finder_mask=mask)
+        if cuts is None:
+            return csr_from_find(*mf.FindAndUpdate())
+        offs, ds, ls, base = [np.zeros(1, np.uint64)], [], [], 0
+        for i, (b, e) in enumerate(zip(cuts[:-1], cuts[1:])):
+            off, st = mf.FindAndUpdate(b, e, slot=i & 1)
+            offs.append(off[1:].astype(np.uint64) + base)
+            base += int(off[-1])
+            ds.append(st["dist"].copy())
+            ls.append(st["len"].copy())
+        return np.concatenate(offs), np.concatenate(ds), np.concatenate(ls)
+
+
+@pytest.mark.parametrize("kind,n,hb", [("text", 250_000, 24), ("text", 200_000, 15), ("longrange", 350_000, 24),
+                                       ("longrange", 300_000, 16), ("mixed", 250_000, 16), ("zeros", 60_000, 15),
+                                       ("random", 100_000, 20)])
+def test_emu_all_finders(emu_lib, orc, kind, n, hb):
+    from nlzm_b200 import synth
+    x = synth.make(kind, n)
+    ref = orc.find(x, hb, orc.F_ALL)
+    got = _run(emu_lib, x, hb)
+    assert orc.csr_equal(ref, got), orc.first_diff(ref, got)
+
+
+@pytest.mark.parametrize("mask", [1, 2, 4, 8])
+def test_emu_each_finder(emu_lib, orc, mask):
+    from nlzm_b200 import synth
+    x = np.concatenate([synth.text(100_000, 21), synth.longrange(200_000, 22), synth.mixed(80_000, 23)])
+    ref = orc.find(x, 15, mask)
+    got = _run(emu_lib, x, 15, mask)
+    assert orc.csr_equal(ref, got), orc.first_diff(ref, got)
+
+
+def test_emu_block_mode(emu_lib, orc):
+    from nlzm_b200 import synth
+    x = synth.longrange(300_000, 31)
+    n = x.size
+    for hb in (15, 24):
+        ref = orc.find(x, hb, orc.F_ALL)
+        for cuts in ([0, n // 3, 2 * n // 3 + 17, n], [0, 1000, n - 5, n], [0, n - 2, n]):
+            got = _run(emu_lib, x, hb, 15, cuts)
+            assert orc.csr_equal(ref, got), (hb, cuts)
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 4, 5, 255, 256, 257, 300, 1000])
+def test_emu_tiny(emu_lib, orc, n):
+    from nlzm_b200 import synth
+    x = synth.text(max(n, 1), 3)[:n]
+    ref = orc.find(x, 15, orc.F_ALL) if n else (np.zeros(1, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.uint16))
+    assert orc.csr_equal(ref, _run(emu_lib, x, 15))
+
+
+def test_emu_golden(emu_lib, orc):
+    """committed fixtures that came from the reference's real encoder"""
+    import glob, os
+    from conftest import ROOT
+    for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "small_*.npz")))[:3]:
+        z = np.load(path)
+        ref = orc.records_to_csr(z["x"].size, z["pos"], z["dist"], z["len"])
+        got = _run(emu_lib, z["x"], int(z["hist_bits"]))
+        assert orc.csr_equal(ref, got), os.path.basename(path)
+
+
+def test_error_paths(emu_lib):
+    from nlzm_b200.matchfinder import MatchFinders, MatchFinderError
+    mf = MatchFinders(emu_lib)
+    mf.Init(15, np.zeros(100, np.uint8))
+    with pytest.raises(MatchFinderError):
+        mf.FindAndUpdate(50, 200)
+    with pytest.raises(MatchFinderError):
+        mf.FindAndUpdate(0, 10, slot=3)
+    with pytest.raises(MatchFinderError):
+        mf.fetch(0)
+    mf.Release()

@@ -1,0 +1,63 @@
+"""Multi-GPU host logic on CPU: one process per rank (gloo, world_size 2), positions sharded, no
+data-path collective — each rank finds its own range (with the window halo behind it), rank 0 gathers
+the per-rank results and they must equal the whole-file oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+    from nlzm_b200 import _lib, synth, sharding
+    from nlzm_b200.matchfinder import MatchFinders
+    emu = _lib.bind_prototypes(C.CDLL(os.path.join(ROOT, "tests", "emu", "libnlzm_mf_emu.so")))
+    x = synth.longrange(260_000, 91)                     # replicated input
+    b, e = sharding.shard_range(x.size, rank, world)
+    with MatchFinders(emu) as mf:
+        mf.Init(15, x)
+        off, st = mf.FindAndUpdate(b, e)
+    parts = [None] * world
+    dist.gather_object((b, e, off, st), parts if rank == 0 else None, dst=0)
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)             # the bench's max-over-ranks timing pattern
+    if rank == 0:
+        q.put((parts, float(t)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding(emu_lib, orc):
+    from nlzm_b200 import synth, sharding
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    parts, tmax = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert tmax == 2.0
+    x = synth.longrange(260_000, 91)
+    off, dist_, ln = sharding.concat_views([(b, e, o, s) for (b, e, o, s) in parts])
+    ref = orc.find(x, 15, orc.F_ALL)
+    assert orc.csr_equal(ref, (off, dist_, ln))
+
+
+def test_shard_ranges_cover():
+    from nlzm_b200 import sharding
+    for n in (0, 1, 1000, 100_000_000, 1_000_000_007):
+        for w in (1, 2, 4, 8):
+            r = [sharding.shard_range(n, i, w) for i in range(w)]
+            assert r[0][0] == 0 and r[-1][1] == n
+            assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))

@@ -1,6 +1,6 @@
 # scratch: first timing of the engine on the GPU box
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nlzm_b200 import synth
 from nlzm_b200.matchfinder import MatchFinders, profile, kernel_times
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
