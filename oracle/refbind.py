@@ -91,3 +91,30 @@ def matchfind(x: np.ndarray, hist_bits: int, finder_mask: int = 0xF, mode=R2, us
     secs = L.ref_matchfind(buf.ctypes.data, x.size, hist_bits, finder_mask, int(use_carry), C.byref(upd))
     L.ref_set_dump(0)
     return _take_dump(), secs
+
+
+# ---- the reference's parser + coder fed by the engine through the host shim (integration demo) ----
+REF_GPU_SO = os.path.join(_HERE, "_ref", "libnlzm_ref_gpu.so")
+REF_EMU_SO = os.path.join(_HERE, "_ref", "libnlzm_ref_emu.so")
+
+
+def engine_fed_encode(in_path: str, out_path: str, hist_bits: int, emu: bool = False, device: int = 0,
+                      block_len: int = 0):
+    """Returns (seconds, steps_served). emu=True links the sequential emulation (CPU-only check)."""
+    path = REF_EMU_SO if emu else REF_GPU_SO
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} missing: run `make -C oracle gpu` where /root/reference exists")
+    L = C.CDLL(path)
+    L.refgpu_encode.argtypes = [C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_uint64, C.POINTER(C.c_double),
+                                C.POINTER(C.c_uint64)]
+    secs, served = C.c_double(0), C.c_uint64(0)
+    rc = L.refgpu_encode(in_path.encode(), out_path.encode(), hist_bits, device, block_len, C.byref(secs), C.byref(served))
+    if rc:
+        raise RuntimeError(f"refgpu_encode rc={rc}")
+    return secs.value, served.value
+
+
+def r0_cli(*args) -> str:
+    """Run the pristine reference binary (oracle/_ref/nlzm_r0)."""
+    import subprocess
+    return subprocess.run([REF_R0, *args], check=True, capture_output=True, text=True).stdout
