@@ -10,6 +10,14 @@
 // side via "next greater position" pointers (ng). Along such a chain positions get nearer to a
 // and lcp(., a) never grows, so the walk stops at the first element that does not beat best[a],
 // the longest match already found at nearer levels.
+//
+// Two kernels do the levels:
+//   k_dc_base        one CTA per tile of 2^BASE_LOG positions: text, ranks, level arrays and pointers
+//                    live in shared memory for the first BASE_LOG levels
+//   k_dc_merge_tile  one level above that: merge-path tiles of 1024 elements staged in shared memory,
+//                    coalesced in and out; elements carry their first 22 bytes and their best length,
+//                    so most candidate tests never touch the text
+//   k_dc_partition   merge-path diagonals for k_dc_merge_tile; k_dc_link: pg/ng maintenance
 #pragma once
 #include "common.cuh"
 
@@ -20,6 +28,15 @@ struct PtrEntry {
 };
 #define NLZM_PG_NONE 0ull
 #define NLZM_NG_NONE 0xFFFFFFFFFFFFFFFFull
+
+// Level-array element: 32 bytes, streamed once in and once out per level.
+struct Elem {
+    u64 key;    // rank << 32 | universe-relative position: strict total order of the suffixes
+    u64 p0;     // text bytes 0..7 of the suffix (little endian: byte 0 in the low bits)
+    u64 p1;     // text bytes 8..15
+    u64 tail;   // text bytes 16..21 in bits 0..47, best match length so far in bits 48..63
+};
+#define NLZM_ELEM_PREFIX 22u
 
 struct TupleSink {
     u64 *keys;       // (a_rel << 9) | len
@@ -47,120 +64,469 @@ DEV void tuple_append(const TupleSink &s, u32 a_rel, u32 dist, u32 len) {
     }
 }
 
-struct LevelParams {
-    const u64 *cur;      // level k-1 arrays: each aligned segment of h elements sorted by key
-    u64 *nxt;            // level k arrays
-    u32 *corank;         // per cur index of a left-half element: its co-rank in the right half
-    PtrEntry *ptr;       // indexed by universe-relative position
-    u16 *best;           // indexed by universe-relative position
+struct DcParams {
     const u8 *x;         // whole input, absolute
     Geom g;
     u64 u0;              // absolute offset of the universe
     u64 own_b, own_e;    // absolute range whose candidates are wanted
     u32 n;               // universe size
-    u32 h;               // half segment size at this level
+    u32 h;               // half segment size at this level (merge levels)
+    const u32 *rank;     // stage S output (base kernel only)
+    const Elem *cur;     // level k-1 arrays
+    Elem *nxt;           // level k arrays
+    u32 *corank;         // per cur index of a left-half element: its co-rank in the right half
+    const u32 *part;     // merge-path split per output tile (merge levels)
+    PtrEntry *ptr;       // indexed by universe-relative position
     TupleSink sink;
 };
 
-HD u32 lower_bound_u64(const u64 *__restrict__ a, u32 n, u64 key) {
+DEV void dc_emit(const DcParams &p, u64 a_abs, u32 dist, u32 len) {
+    if (dist <= p.g.W - 1 && len >= match_min(dist)) tuple_append(p.sink, (u32)(a_abs - p.own_b), dist, len);
+}
+
+// can position a_abs be a query at all, and with which length cap
+DEV bool dc_query_cap(const DcParams &p, u64 a_abs, u32 &cap) {
+    if (a_abs < p.own_b || a_abs >= p.own_e) return false;
+    const u64 left_in_file = p.g.flen - a_abs;
+    if (left_in_file < 4) return false;                                   // HT/BT need 4 visible bytes (NLZM.cpp:1515)
+    cap = left_in_file < NLZM_MATCH_MAX ? (u32)left_in_file : NLZM_MATCH_MAX;   // NLZM.cpp:987
+    return true;
+}
+
+// ================================================================================================
+// base kernel: levels 1..BASE_LOG inside shared memory
+// ================================================================================================
+#ifndef NLZM_BASE_LOG
+#define NLZM_BASE_LOG 12
+#endif
+#define NLZM_BASE_TILE (1u << NLZM_BASE_LOG)
+#define NLZM_BASE_IPT 8u
+#define NLZM_BASE_THREADS (NLZM_BASE_TILE / NLZM_BASE_IPT)
+#define NLZM_BASE_TEXT (NLZM_BASE_TILE + NLZM_MATCH_MAX + 8)
+#define NLZM_BASE_SMEM (NLZM_BASE_TILE * 20 + NLZM_BASE_TEXT + 8)
+#define NLZM_L16_NONE 0xFFFFu
+
+struct BaseSmem {
+    u32 *rnk;        // rank of local position
+    u32 *k4;         // first 4 text bytes of local position
+    u16 *arr[2];     // level arrays: local positions sorted by (rank, position) inside each segment
+    u16 *pg, *ng;    // greater-position pointers as local positions
+    u16 *best;       // best length per local position
+    u16 *cor;        // co-rank in the sibling half, per array index
+    u8 *text;        // tile text + lookahead
+};
+
+DEV BaseSmem base_carve(u8 *smem) {
+    BaseSmem s;
+    s.rnk = (u32 *)smem;
+    s.k4 = s.rnk + NLZM_BASE_TILE;
+    s.arr[0] = (u16 *)(s.k4 + NLZM_BASE_TILE);
+    s.arr[1] = s.arr[0] + NLZM_BASE_TILE;
+    s.pg = s.arr[1] + NLZM_BASE_TILE;
+    s.ng = s.pg + NLZM_BASE_TILE;
+    s.best = s.ng + NLZM_BASE_TILE;
+    s.cor = s.best + NLZM_BASE_TILE;
+    s.text = (u8 *)(s.cor + NLZM_BASE_TILE);
+    return s;
+}
+
+DEV bool base_less(const BaseSmem &s, u32 a, u32 b) {       // (rank, position) order; ranks tie only for equal prefixes
+    const u32 ra = s.rnk[a], rb = s.rnk[b];
+    return ra < rb || (ra == rb && a < b);
+}
+
+DEV u32 base_lower_bound(const BaseSmem &s, const u16 *arr, u32 n, u32 pos) {
     u32 lo = 0, hi = n;
     while (lo < hi) {
-        u32 mid = (lo + hi) >> 1;
-        if (a[mid] < key) lo = mid + 1; else hi = mid;
+        const u32 mid = (lo + hi) >> 1;
+        if (base_less(s, arr[mid], pos)) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
-// Walk one greater-position chain of the left half and emit the candidates that beat best_in.
-DEV void dc_walk(const LevelParams &p, u32 a_rel_u, u64 a_abs, u32 cap, u32 best_in, u64 start_key, bool left,
-                 u32 &new_best) {
-    const u32 none_lo = left ? 0u : 0xFFFFFFFFu;
-    if (start_key == (left ? NLZM_PG_NONE : NLZM_NG_NONE)) return;
-    (void)none_lo;
-    u32 c = (u32)start_key;
-    u32 pend_len = 0, pend_c = 0;
-    u32 lim = cap;
-    const u32 a_rel = (u32)(a_abs - p.own_b);
-    while (true) {
-        u32 l = lcp_cap(p.x, p.u0 + c, a_abs, lim);
+// merge-path split inside shared memory: left elements among the first d outputs of the segment
+DEV u32 base_merge_path(const BaseSmem &s, const u16 *L, u32 l_len, const u16 *R, u32 r_len, u32 d) {
+    u32 lo = d > r_len ? d - r_len : 0, hi = d < l_len ? d : l_len;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (base_less(s, L[mid], R[d - 1 - mid])) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Walk one chain; the caller has already established that the first 4 bytes of `start` match.
+DEV void base_walk(const DcParams &p, const BaseSmem &s, u32 a, u64 a_abs, u32 cap, u32 best_in, u32 start, const u16 *link,
+                   u32 &new_best) {
+    u32 c = start, pend_len = 0, pend_c = 0, lim = cap;
+    const u32 ka = s.k4[a];
+    while (c != NLZM_L16_NONE) {
+        if (s.k4[c] != ka) break;                          // lcp < 4 can never beat best (>= 3)
+        u32 l = 4;
+        while (l < lim && s.text[c + l] == s.text[a + l]) ++l;
+        if (l > lim) l = lim;
         if (l <= best_in) break;
-        if (pend_len && l < pend_len) {
-            u32 d = a_rel_u - pend_c;
-            if (d <= p.g.W - 1 && pend_len >= match_min(d)) tuple_append(p.sink, a_rel, d, pend_len);
-        }
+        if (pend_len && l < pend_len) dc_emit(p, a_abs, a - pend_c, pend_len);
         pend_len = l; pend_c = c;       // equal lcp: the nearer element replaces the farther one
         lim = l;                        // lcp never grows along the chain
         if (l > new_best) new_best = l;
-        u64 k = left ? p.ptr[c].pg : p.ptr[c].ng;
+        c = link[c];
+    }
+    if (pend_len) dc_emit(p, a_abs, a - pend_c, pend_len);
+}
+
+DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
+    const BaseSmem s = base_carve(smem);
+    const u32 t0 = bid * NLZM_BASE_TILE;
+    const u32 m = (p.n - t0) < NLZM_BASE_TILE ? (p.n - t0) : NLZM_BASE_TILE;
+    const u64 abs0 = p.u0 + t0;
+    const u64 x_end = p.g.flen + NLZM_X_PAD;                 // bytes [flen, x_end) are zero padding
+    for (u32 i = tid; i < NLZM_BASE_TEXT; i += NLZM_BASE_THREADS) s.text[i] = (abs0 + i < x_end) ? p.x[abs0 + i] : (u8)0;
+    for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
+        s.rnk[i] = p.rank[t0 + i];
+        s.arr[0][i] = (u16)i;
+        s.pg[i] = NLZM_L16_NONE;
+        s.ng[i] = NLZM_L16_NONE;
+        s.best[i] = 3;
+    }
+    NLZM_CTA_SYNC();
+    for (u32 i = tid; i < m; i += NLZM_BASE_THREADS)
+        s.k4[i] = (u32)s.text[i] | ((u32)s.text[i + 1] << 8) | ((u32)s.text[i + 2] << 16) | ((u32)s.text[i + 3] << 24);
+    NLZM_CTA_SYNC();
+    u32 cur = 0;
+    for (u32 h = 1; h < m; h <<= 1) {
+        const u16 *A = s.arr[cur];
+        u16 *B = s.arr[cur ^ 1];
+        // ---- phase A: merge by co-rank; cor[i] = co-rank of A[i] in the sibling half
+        if (2 * h < NLZM_BASE_IPT) {
+            for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
+                const u32 pos = A[i];
+                const u32 base = i & ~(2 * h - 1);
+                const u32 l_len = (m - base) < h ? (m - base) : h;
+                const u32 r_beg = base + l_len;
+                const u32 r_len = (m - r_beg) < h ? (m - r_beg) : h;
+                if (r_len == 0) { B[i] = (u16)pos; continue; }
+                if (i < r_beg) {
+                    const u32 u = base_lower_bound(s, A + r_beg, r_len, pos);
+                    s.cor[i] = (u16)u;
+                    B[i + u] = (u16)pos;
+                } else {
+                    const u32 t = base_lower_bound(s, A + base, l_len, pos);
+                    s.cor[i] = (u16)t;
+                    B[base + (i - r_beg) + t] = (u16)pos;
+                }
+            }
+        } else {
+            // each thread produces NLZM_BASE_IPT consecutive outputs of one segment (IPT divides 2h)
+            const u32 o_beg = tid * NLZM_BASE_IPT;
+            if (o_beg < m) {
+                const u32 base = o_beg & ~(2 * h - 1);
+                const u32 l_len = (m - base) < h ? (m - base) : h;
+                const u32 r_beg = base + l_len;
+                const u32 r_len = (m - r_beg) < h ? (m - r_beg) : h;
+                const u32 o_end = (o_beg + NLZM_BASE_IPT) < (r_beg + r_len) ? (o_beg + NLZM_BASE_IPT) : (r_beg + r_len);
+                if (r_len == 0) {
+                    for (u32 o = o_beg; o < o_end; o++) B[o] = A[o];
+                } else {
+                    u32 li = base_merge_path(s, A + base, l_len, A + r_beg, r_len, o_beg - base);
+                    u32 ri = (o_beg - base) - li;
+                    u32 pl = li < l_len ? A[base + li] : 0, pr = ri < r_len ? A[r_beg + ri] : 0;
+                    u32 rl = li < l_len ? s.rnk[pl] : 0, rr = ri < r_len ? s.rnk[pr] : 0;
+                    for (u32 o = o_beg; o < o_end; o++) {
+                        const bool take_l = (ri >= r_len) || (li < l_len && (rl < rr || (rl == rr && pl < pr)));
+                        if (take_l) {
+                            B[o] = (u16)pl;
+                            s.cor[base + li] = (u16)ri;
+                            ++li;
+                            if (li < l_len) { pl = A[base + li]; rl = s.rnk[pl]; }
+                        } else {
+                            B[o] = (u16)pr;
+                            s.cor[r_beg + ri] = (u16)li;
+                            ++ri;
+                            if (ri < r_len) { pr = A[r_beg + ri]; rr = s.rnk[pr]; }
+                        }
+                    }
+                }
+            }
+        }
+        NLZM_CTA_SYNC();
+        // ---- phase Q: right-half elements query the left half
+        for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
+            const u32 base = i & ~(2 * h - 1);
+            const u32 l_len = (m - base) < h ? (m - base) : h;
+            const u32 r_beg = base + l_len;
+            if (i < r_beg || r_beg >= m) continue;
+            const u32 pos = A[i], t = s.cor[i];
+            const u32 cl = t > 0 ? A[base + t - 1] : NLZM_L16_NONE;
+            const u32 cr = t < l_len ? A[base + t] : NLZM_L16_NONE;
+            const u32 ka = s.k4[pos];
+            const bool hit_l = cl != NLZM_L16_NONE && s.k4[cl] == ka;
+            const bool hit_r = cr != NLZM_L16_NONE && s.k4[cr] == ka;
+            if (!hit_l && !hit_r) continue;
+            u32 cap;
+            const u64 a_abs = abs0 + pos;
+            if (!dc_query_cap(p, a_abs, cap)) continue;
+            const u32 best_in = s.best[pos];
+            if (best_in >= cap) continue;
+            u32 nb = best_in;
+            if (hit_l) base_walk(p, s, pos, a_abs, cap, best_in, cl, s.pg, nb);
+            if (hit_r) base_walk(p, s, pos, a_abs, cap, best_in, cr, s.ng, nb);
+            if (nb != best_in) s.best[pos] = (u16)nb;
+        }
+        NLZM_CTA_SYNC();
+        // ---- phase B: left-half elements adopt their rank-nearest right neighbours when nearer in rank
+        for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
+            const u32 base = i & ~(2 * h - 1);
+            const u32 l_len = (m - base) < h ? (m - base) : h;
+            const u32 r_beg = base + l_len;
+            if (i >= r_beg) continue;
+            const u32 r_len = (m - r_beg) < h ? (m - r_beg) : h;
+            if (r_len == 0) continue;
+            const u32 pos = A[i], u = s.cor[i];
+            if (u > 0) { const u32 r = A[r_beg + u - 1]; const u32 o = s.pg[pos]; if (o == NLZM_L16_NONE || base_less(s, o, r)) s.pg[pos] = (u16)r; }
+            if (u < r_len) { const u32 r = A[r_beg + u]; const u32 o = s.ng[pos]; if (o == NLZM_L16_NONE || base_less(s, r, o)) s.ng[pos] = (u16)r; }
+        }
+        NLZM_CTA_SYNC();
+        cur ^= 1;
+    }
+    // hand over to the merge levels: fat elements in rank order, pointers by position
+    const u16 *A = s.arr[cur];
+    for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
+        const u32 pos = A[i];
+        const u8 *t = s.text + pos;
+        Elem e;
+        e.key = ((u64)s.rnk[pos] << 32) | (t0 + pos);
+        u64 a = 0, b = 0, c = 0;
+        #pragma unroll
+        for (int k = 0; k < 8; k++) { a |= (u64)t[k] << (8 * k); b |= (u64)t[8 + k] << (8 * k); }
+        #pragma unroll
+        for (int k = 0; k < 6; k++) c |= (u64)t[16 + k] << (8 * k);
+        e.p0 = a; e.p1 = b;
+        e.tail = c | ((u64)s.best[pos] << 48);
+        p.nxt[t0 + i] = e;
+        PtrEntry pe;
+        const u32 g0 = s.pg[i], g1 = s.ng[i];
+        pe.pg = g0 == NLZM_L16_NONE ? NLZM_PG_NONE : (((u64)s.rnk[g0] << 32) | (t0 + g0));
+        pe.ng = g1 == NLZM_L16_NONE ? NLZM_NG_NONE : (((u64)s.rnk[g1] << 32) | (t0 + g1));
+        p.ptr[t0 + i] = pe;
+    }
+}
+NLZM_KERNEL_CTA(dc_base, DcParams, NLZM_BASE_THREADS)
+
+// ================================================================================================
+// merge levels
+// ================================================================================================
+#define NLZM_MT_THREADS 256
+#define NLZM_MT_ITEMS 4
+#define NLZM_MT_TILE (NLZM_MT_THREADS * NLZM_MT_ITEMS)
+#define NLZM_MT_SMEM ((NLZM_MT_TILE + 2) * 32 + NLZM_MT_TILE * 8 + 16)
+
+struct alignas(16) V16 { u64 a, b; };
+
+struct SegGeom { u32 base, l_len, r_beg, r_len; };
+DEV SegGeom seg_geom(u32 n, u32 h, u32 idx) {
+    SegGeom s;
+    s.base = (idx / (2 * h)) * (2 * h);          // 2h <= 2^31 guaranteed by the host loop (h < n < 2^31)
+    s.l_len = (n - s.base) < h ? (n - s.base) : h;
+    s.r_beg = s.base + s.l_len;
+    s.r_len = (n - s.r_beg) < h ? (n - s.r_beg) : h;
+    return s;
+}
+
+// merge-path split: number of left elements among the first d merged outputs of a segment
+DEV u32 merge_path(const Elem *L, u32 l_len, const Elem *R, u32 r_len, u32 d) {
+    u32 lo = d > r_len ? d - r_len : 0, hi = d < l_len ? d : l_len;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (L[mid].key < R[d - 1 - mid].key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// one thread per output tile boundary
+DEV void dc_partition_body(const DcParams &p, u64 j) {
+    const u32 o = (u32)j * NLZM_MT_TILE;
+    const SegGeom s = seg_geom(p.n, p.h, o);
+    u32 *part = (u32 *)p.part;
+    part[j] = s.r_len ? merge_path(p.cur + s.base, s.l_len, p.cur + s.r_beg, s.r_len, o - s.base) : (o - s.base);
+}
+NLZM_KERNEL_1D(dc_partition, DcParams)
+
+// lcp of the suffixes behind two elements from their 22-byte prefixes (22 = "at least 22")
+DEV u32 elem_prefix_lcp(const Elem &a, const Elem &b) {
+    u64 d = a.p0 ^ b.p0;
+    if (d) return (u32)nlzm_ctz64(d) >> 3;
+    d = a.p1 ^ b.p1;
+    if (d) return 8 + ((u32)nlzm_ctz64(d) >> 3);
+    d = (a.tail ^ b.tail) & 0xFFFFFFFFFFFFull;
+    if (d) return 16 + ((u32)nlzm_ctz64(d) >> 3);
+    return NLZM_ELEM_PREFIX;
+}
+
+// lcp of text at c_abs with the suffix of element a (prefix in registers), capped at lim
+DEV u32 elem_text_lcp(const DcParams &p, const Elem &a, u64 a_abs, u64 c_abs, u32 lim) {
+    u32 m;
+    u64 d = load8(p.x, c_abs) ^ a.p0;
+    if (d) m = (u32)nlzm_ctz64(d) >> 3;
+    else {
+        d = load8(p.x, c_abs + 8) ^ a.p1;
+        if (d) m = 8 + ((u32)nlzm_ctz64(d) >> 3);
+        else {
+            d = (load8(p.x, c_abs + 16) ^ a.tail) & 0xFFFFFFFFFFFFull;
+            if (d) m = 16 + ((u32)nlzm_ctz64(d) >> 3);
+            else m = lim > NLZM_ELEM_PREFIX ? NLZM_ELEM_PREFIX + lcp_cap(p.x, c_abs + NLZM_ELEM_PREFIX, a_abs + NLZM_ELEM_PREFIX, lim - NLZM_ELEM_PREFIX) : NLZM_ELEM_PREFIX;
+        }
+    }
+    return m < lim ? m : lim;
+}
+
+// Walk one greater-position chain of the left half; the first element is a neighbour whose element
+// (with prefix) is at hand, the following ones are reached through ptr[] and compared against text.
+DEV void dc_walk(const DcParams &p, const Elem &ea, u64 a_abs, u32 cap, u32 best_in, const Elem *first, bool left, u32 &new_best) {
+    if (!first) return;
+    const u32 a_rel = (u32)ea.key;
+    u32 c = (u32)first->key;
+    u32 l = elem_prefix_lcp(ea, *first);
+    if (l >= NLZM_ELEM_PREFIX && cap > NLZM_ELEM_PREFIX)
+        l = NLZM_ELEM_PREFIX + lcp_cap(p.x, p.u0 + c + NLZM_ELEM_PREFIX, a_abs + NLZM_ELEM_PREFIX, cap - NLZM_ELEM_PREFIX);
+    if (l > cap) l = cap;
+    u32 pend_len = 0, pend_c = 0;
+    while (true) {
+        if (l <= best_in) break;
+        if (pend_len && l < pend_len) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
+        pend_len = l; pend_c = c;
+        if (l > new_best) new_best = l;
+        const u64 k = left ? p.ptr[c].pg : p.ptr[c].ng;
         if (k == (left ? NLZM_PG_NONE : NLZM_NG_NONE)) break;
         c = (u32)k;
+        l = elem_text_lcp(p, ea, a_abs, p.u0 + c, l);        // lcp never grows along the chain
     }
-    if (pend_len) {
-        u32 d = a_rel_u - pend_c;
-        if (d <= p.g.W - 1 && pend_len >= match_min(d)) tuple_append(p.sink, a_rel, d, pend_len);
-    }
+    if (pend_len) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
 }
 
-// Kernel A: merge by co-rank (binary search in the sibling half) + queries of right-half elements.
-DEV void dc_merge_query_body(const LevelParams &p, u64 idx64) {
-    const u32 idx = (u32)idx64;
-    const u64 key = p.cur[idx];
-    const u32 two_h = p.h << 1;                 // h <= 2^31 is guaranteed by the caller
-    const u32 base = (idx / two_h) * two_h;
-    const u32 l_len = (p.n - base) < p.h ? (p.n - base) : p.h;
-    const u32 r_beg = base + l_len;
-    const u32 r_len = (p.n - r_beg) < p.h ? (p.n - r_beg) : p.h;
-    if (r_len == 0) { p.nxt[idx] = key; return; }
-    if (idx < r_beg) {
-        u32 u = lower_bound_u64(p.cur + r_beg, r_len, key);
-        p.corank[idx] = u;
-        p.nxt[idx + u] = key;
+// One CTA produces NLZM_MT_TILE consecutive elements of the merged level array:
+//   load (coalesced) -> merge path on keys -> neighbour tests on the carried prefixes -> the few
+//   elements that found something walk their chains (compacted, all lanes busy) -> store (coalesced)
+DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
+    Elem *el = (Elem *)smem;                                    // [0] left halo, [1..nl] left part, [nl+1] halo, then right part
+    u16 *src = (u16 *)(smem + (NLZM_MT_TILE + 2) * 32);         // output -> slot in el[]
+    u16 *lcnt = src + NLZM_MT_TILE;                             // output (right elements) -> left elements before it
+    u16 *pos_l = lcnt + NLZM_MT_TILE;                           // left element -> output
+    u16 *act = pos_l + NLZM_MT_TILE;                            // outputs that need a chain walk
+    u32 *act_n = (u32 *)(act + NLZM_MT_TILE);
+
+    const u32 o0 = bid * NLZM_MT_TILE;
+    const SegGeom s = seg_geom(p.n, p.h, o0);
+    const u32 seg_end = s.r_beg + s.r_len;
+    const u32 o1 = (o0 + NLZM_MT_TILE) < seg_end ? (o0 + NLZM_MT_TILE) : seg_end;
+    const u32 cnt = o1 - o0;
+    if (s.r_len == 0) {                                         // lonely left half at the end of the universe
+        for (u32 i = tid; i < cnt; i += NLZM_MT_THREADS) p.nxt[o0 + i] = p.cur[o0 + i];
         return;
     }
-    const u32 t = lower_bound_u64(p.cur + base, l_len, key);
-    p.nxt[base + (idx - r_beg) + t] = key;
+    const u32 d0 = o0 - s.base, d1 = o1 - s.base;
+    const u32 l0 = p.part[bid];
+    const u32 l1 = (o1 < seg_end) ? p.part[bid + 1] : s.l_len;
+    const u32 r0 = d0 - l0, r1 = d1 - l1;
+    const u32 nl = l1 - l0, nr = r1 - r0;
+    Elem *SL = el + 1;
+    Elem *SR = el + nl + 2;
+    {
+        // coalesced 16-byte loads: left part with one halo element on each side, then the right part
+        const V16 *GL = (const V16 *)(p.cur + s.base), *GR = (const V16 *)(p.cur + s.r_beg);
+        V16 *S = (V16 *)el;
+        for (u32 c = tid; c < (nl + 2) * 2; c += NLZM_MT_THREADS) {
+            const i64 gi = (i64)l0 + (i64)(c >> 1) - 1;
+            if (gi >= 0 && gi < (i64)s.l_len) S[c] = GL[gi * 2 + (c & 1)];
+        }
+        V16 *S2 = (V16 *)SR;
+        for (u32 c = tid; c < nr * 2; c += NLZM_MT_THREADS) S2[c] = GR[(u64)r0 * 2 + c];
+    }
+    if (tid == 0) *act_n = 0;
+    NLZM_CTA_SYNC();
 
-    const u32 pos = (u32)key;
-    const u64 a_abs = p.u0 + pos;
-    if (a_abs < p.own_b || a_abs >= p.own_e) return;
-    const u64 left_in_file = p.g.flen - a_abs;
-    if (left_in_file < 4) return;                                   // HT/BT need 4 visible bytes (NLZM.cpp:1515)
-    const u32 cap = left_in_file < NLZM_MATCH_MAX ? (u32)left_in_file : NLZM_MATCH_MAX;   // NLZM.cpp:987
-    const u32 best_in = p.best[pos];
-    if (best_in >= cap) return;                                     // already matched to the cap at a nearer level
-    if (pos - (r_beg - 1) > p.g.W - 1) return;                      // the whole left half is outside the window
-    u32 nb = best_in;
-    dc_walk(p, pos, a_abs, cap, best_in, t > 0 ? p.cur[base + t - 1] : NLZM_PG_NONE, true, nb);
-    dc_walk(p, pos, a_abs, cap, best_in, t < l_len ? p.cur[base + t] : NLZM_NG_NONE, false, nb);
-    if (nb != best_in) p.best[pos] = (u16)nb;
+    // ---- merge path on keys: NLZM_MT_ITEMS outputs per thread
+    {
+        const u32 t_d = tid * NLZM_MT_ITEMS < cnt ? tid * NLZM_MT_ITEMS : cnt;
+        const u32 t_e = t_d + NLZM_MT_ITEMS < cnt ? t_d + NLZM_MT_ITEMS : cnt;
+        u32 li = merge_path(SL, nl, SR, nr, t_d), ri = t_d - li;
+        u64 kl = li < nl ? SL[li].key : 0, kr = ri < nr ? SR[ri].key : 0;
+        for (u32 o = t_d; o < t_e; o++) {
+            const bool take_l = (ri >= nr) || (li < nl && kl < kr);
+            if (take_l) {
+                src[o] = (u16)(1 + li);
+                pos_l[li] = (u16)o;
+                ++li;
+                if (li < nl) kl = SL[li].key;
+            } else {
+                src[o] = (u16)(nl + 2 + ri);
+                lcnt[o] = (u16)li;
+                ++ri;
+                if (ri < nr) kr = SR[ri].key;
+            }
+        }
+    }
+    NLZM_CTA_SYNC();
+
+    // ---- neighbour tests from the carried prefixes; survivors go to the active list
+    for (u32 o = tid; o < cnt; o += NLZM_MT_THREADS) {
+        const u32 slot = src[o];
+        if (slot < nl + 2) continue;                            // left element: nothing to query
+        const Elem &e = el[slot];
+        const u32 pos = (u32)e.key;
+        const u64 a_abs = p.u0 + pos;
+        u32 cap;
+        const u32 best_in = (u32)(e.tail >> 48);
+        if (!dc_query_cap(p, a_abs, cap) || best_in >= cap || pos - (s.r_beg - 1) > p.g.W - 1) continue;
+        const u32 li = lcnt[o];
+        bool want = false;
+        if (l0 + li > 0) { u32 l = elem_prefix_lcp(e, el[li]); l = l < cap ? l : cap; want |= (l > best_in) || (l >= NLZM_ELEM_PREFIX && cap > NLZM_ELEM_PREFIX); }
+        if (l0 + li < s.l_len) { u32 l = elem_prefix_lcp(e, el[li + 1]); l = l < cap ? l : cap; want |= (l > best_in) || (l >= NLZM_ELEM_PREFIX && cap > NLZM_ELEM_PREFIX); }
+        if (want) act[nlzm_atomic_add(act_n, 1u)] = (u16)o;
+    }
+    NLZM_CTA_SYNC();
+
+    // ---- chain walks of the active elements
+    const u32 n_act = *act_n;
+    for (u32 k = tid; k < n_act; k += NLZM_MT_THREADS) {
+        const u32 o = act[k];
+        Elem &e = el[src[o]];
+        const Elem ea = e;
+        const u32 pos = (u32)ea.key;
+        const u64 a_abs = p.u0 + pos;
+        u32 cap = 0;
+        dc_query_cap(p, a_abs, cap);
+        const u32 best_in = (u32)(ea.tail >> 48);
+        const u32 li = lcnt[o];
+        u32 nb = best_in;
+        dc_walk(p, ea, a_abs, cap, best_in, (l0 + li > 0) ? &el[li] : nullptr, true, nb);
+        dc_walk(p, ea, a_abs, cap, best_in, (l0 + li < s.l_len) ? &el[li + 1] : nullptr, false, nb);
+        if (nb != best_in) e.tail = (ea.tail & 0xFFFFFFFFFFFFull) | ((u64)nb << 48);
+    }
+    NLZM_CTA_SYNC();
+
+    // ---- coalesced stores: merged elements, and the co-rank of every left element
+    {
+        const V16 *S = (const V16 *)el;
+        V16 *G = (V16 *)(p.nxt + o0);
+        for (u32 c = tid; c < cnt * 2; c += NLZM_MT_THREADS) G[c] = S[(u32)src[c >> 1] * 2 + (c & 1)];
+        for (u32 i = tid; i < nl; i += NLZM_MT_THREADS) p.corank[s.base + l0 + i] = r0 + ((u32)pos_l[i] - i);
+    }
 }
-NLZM_KERNEL_1D(dc_merge_query, LevelParams)
+NLZM_KERNEL_CTA(dc_merge_tile, DcParams, NLZM_MT_THREADS)
 
-// Kernel B: left-half elements adopt their rank-nearest right-half neighbours as pg / ng when those
-// are nearer in rank than the pointers they already hold (every right-half position is greater).
-DEV void dc_link_body(const LevelParams &p, u64 idx64) {
+// Left-half elements adopt their rank-nearest right-half neighbours as pg / ng when those are nearer
+// in rank than the pointers they already hold (every right-half position is greater). Separate launch:
+// the queries of a level must read the pointers of the level below.
+DEV void dc_link_body(const DcParams &p, u64 idx64) {
     const u32 idx = (u32)idx64;
-    const u32 two_h = p.h << 1;
-    const u32 base = (idx / two_h) * two_h;
-    const u32 l_len = (p.n - base) < p.h ? (p.n - base) : p.h;
-    const u32 r_beg = base + l_len;
-    if (idx >= r_beg) return;
-    const u32 r_len = (p.n - r_beg) < p.h ? (p.n - r_beg) : p.h;
-    if (r_len == 0) return;
-    const u32 pos = (u32)p.cur[idx];
+    const SegGeom s = seg_geom(p.n, p.h, idx);
+    if (idx >= s.r_beg || s.r_len == 0) return;
+    const u32 pos = (u32)p.cur[idx].key;
     const u32 u = p.corank[idx];
     PtrEntry e = p.ptr[pos];
     bool ch = false;
-    if (u > 0) { u64 k = p.cur[r_beg + u - 1]; if (k > e.pg) { e.pg = k; ch = true; } }
-    if (u < r_len) { u64 k = p.cur[r_beg + u]; if (k < e.ng) { e.ng = k; ch = true; } }
+    if (u > 0) { const u64 k = p.cur[s.r_beg + u - 1].key; if (k > e.pg) { e.pg = k; ch = true; } }
+    if (u < s.r_len) { const u64 k = p.cur[s.r_beg + u].key; if (k < e.ng) { e.ng = k; ch = true; } }
     if (ch) p.ptr[pos] = e;
 }
-NLZM_KERNEL_1D(dc_link, LevelParams)
-
-struct DcInitParams { PtrEntry *ptr; u16 *best; u16 best0; };
-DEV void dc_init_body(const DcInitParams &p, u64 i) {
-    PtrEntry e; e.pg = NLZM_PG_NONE; e.ng = NLZM_NG_NONE;
-    p.ptr[i] = e;
-    p.best[i] = p.best0;
-}
-NLZM_KERNEL_1D(dc_init, DcInitParams)
+NLZM_KERNEL_1D(dc_link, DcParams)

@@ -23,6 +23,10 @@
 #include <vector>
 #include <stdio.h>
 
+#ifdef NLZM_EMU
+thread_local EmuCta nlzm_emu_cta;
+#endif
+
 // ---- launch accounting / per-kernel timing ----------------------------------------------------
 static std::atomic<unsigned long long> g_launches{0};
 struct KernelProf {
@@ -101,11 +105,11 @@ struct nlzm_mf {
     DevBuf x;
     bool have_input = false;
 
-    DevBuf k64[2], v32[2], rank, ptr, best, aux0, aux1;            // stages S/T
+    DevBuf k64[2], v32[2], rank, ptr, aux0, aux1, el[2], part;     // stages S/T
     DevBuf tk[2], tv[2], tcount, keep, out_idx;                    // tuples / merge
     DevBuf e_k[2], e_v[2], e_inv;                                  // HT / BT-short event sorts
     DevBuf hblk, sl_k[2], sl_v[2], sl_cnt, sl_off;                 // RK table
-    DevBuf hit_k[2], hit_v[2], hit_len, hit_count, iv, n_iv;       // RK hits / carry intervals
+    DevBuf hit_k[2], hit_v[2], hit_len, hit_count, iv, n_iv, val_k, val_v;       // RK hits / carry intervals
     DevBuf scalars;                                                // misc device scalars
     PrimTemp tmp;
     DevBuf tmpbuf;
@@ -183,7 +187,7 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
     CKI(ensure(k64[0], n * 8)); CKI(ensure(k64[1], n * 8));
     CKI(ensure(v32[0], n * 4)); CKI(ensure(v32[1], n * 4));
     CKI(ensure(rank, n * 4)); CKI(ensure(aux0, n * 4)); CKI(ensure(aux1, n * 4));
-    CKI(ensure(ptr, n * sizeof(PtrEntry))); CKI(ensure(best, n * 2));
+    CKI(ensure(ptr, n * sizeof(PtrEntry)));
     CKI(ensure_prim(n));
     u64 *sum_dev = scalars.as<u64>();
 
@@ -212,31 +216,37 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
         launch_rank_pair(pp, n, st);
         depth *= 2;
     }
-    RankElemParams ep{rank.as<u32>(), k64[0].as<u64>()};
-    launch_rank_elem(ep, n, st);
     cudaEventRecord(ev1, st);
 
-    // --- T: levels
-    DcInitParams dp{ptr.as<PtrEntry>(), best.as<u16>(), (u16)3};
-    launch_dc_init(dp, n, st);
-    LevelParams lp;
-    lp.corank = rank.as<u32>();          // ranks now live inside the element keys
-    lp.ptr = ptr.as<PtrEntry>();
-    lp.best = best.as<u16>();
-    lp.x = x.as<u8>();
-    lp.g = g;
-    lp.u0 = u0;
-    lp.own_b = own_b;
-    lp.own_e = own_e;
-    lp.n = (u32)n;
-    lp.sink = sink();
+    // --- T: first NLZM_BASE_LOG levels in shared memory, then one merge-path pass per level
+    CKI(ensure(el[0], n * sizeof(Elem))); CKI(ensure(el[1], n * sizeof(Elem)));
+    const u64 tiles = (n + NLZM_MT_TILE - 1) / NLZM_MT_TILE;
+    CKI(ensure(part, (tiles + 2) * 4));
+    DcParams dp;
+    dp.x = x.as<u8>();
+    dp.g = g;
+    dp.u0 = u0;
+    dp.own_b = own_b;
+    dp.own_e = own_e;
+    dp.n = (u32)n;
+    dp.h = 0;
+    dp.rank = rank.as<u32>();
+    dp.cur = nullptr;
+    dp.nxt = el[0].as<Elem>();
+    dp.corank = nullptr;
+    dp.part = part.as<u32>();
+    dp.ptr = ptr.as<PtrEntry>();
+    dp.sink = sink();
+    CKI(launch_dc_base(dp, (n + NLZM_BASE_TILE - 1) / NLZM_BASE_TILE, NLZM_BASE_SMEM, st));
+    dp.corank = rank.as<u32>();          // ranks now live inside the element keys
     int cur = 0;
-    for (u64 h = 1; h < n; h <<= 1) {
-        lp.cur = k64[cur].as<u64>();
-        lp.nxt = k64[cur ^ 1].as<u64>();
-        lp.h = (u32)h;
-        launch_dc_merge_query(lp, n, st);
-        launch_dc_link(lp, n, st);
+    for (u64 h = NLZM_BASE_TILE; h < n; h <<= 1) {
+        dp.cur = el[cur].as<Elem>();
+        dp.nxt = el[cur ^ 1].as<Elem>();
+        dp.h = (u32)h;
+        launch_dc_partition(dp, tiles, st);
+        CKI(launch_dc_merge_tile(dp, tiles, NLZM_MT_SMEM, st));
+        launch_dc_link(dp, n, st);
         cur ^= 1;
     }
 
@@ -340,11 +350,22 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     CK(cudaStreamSynchronize(st));
     if (n_hits > hit_cap) return fail(NLZM_MF_E_OVERFLOW, "RK raw-hit buffer overflow");
     if (n_hits == 0) return 0;
-    int hsel = 0;
-    CKI(prim_sort_pairs64(tmp, hit_k[0].as<u64>(), hit_k[1].as<u64>(), hit_v[0].as<u32>(), hit_v[1].as<u32>(), n_hits, 0, (int)bits_for(g.flen + 1), st, &hsel));
-    RkExtendParams xp{x.as<u8>(), g, hit_k[hsel].as<u64>(), hit_v[hsel].as<u32>(), hit_len.as<u32>()};
+    // extension of every raw hit (any order); the few that are real hits are compacted, sorted by
+    // position and fed to the sequential carry state machine
+    u32 *n_valid = scalars.as<u32>() + 10;
+    CK(cudaMemsetAsync(n_valid, 0, 4, st));
+    RkExtendParams xp{x.as<u8>(), g, hit_k[0].as<u64>(), hit_v[0].as<u32>(), hit_len.as<u32>(),
+                      hit_k[1].as<u64>(), hit_v[1].as<u32>(), n_valid};
     launch_rk_extend(xp, n_hits, st);
-    RkChainParams cp{g, hit_k[hsel].as<u64>(), hit_v[hsel].as<u32>(), hit_len.as<u32>(), hit_count, iv.as<RkInterval>(), n_iv};
+    u32 nv = 0;
+    CK(cudaMemcpyAsync(&nv, n_valid, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (nv == 0) return 0;
+    CKI(ensure(val_k, (u64)nv * 8)); CKI(ensure(val_v, (u64)nv * 4));
+    int hsel = 0;
+    CKI(prim_sort_pairs64(tmp, hit_k[1].as<u64>(), val_k.as<u64>(), hit_v[1].as<u32>(), val_v.as<u32>(), nv, 0, (int)bits_for(g.flen + 1), st, &hsel));
+    RkChainParams cp{g, hsel ? val_k.as<u64>() : hit_k[1].as<u64>(), hsel ? val_v.as<u32>() : hit_v[1].as<u32>(),
+                     hit_v[0].as<u32>(), hit_len.as<u32>(), n_valid, iv.as<RkInterval>(), n_iv};
     launch_rk_chain(cp, 1, st);
     u32 niv = 0;
     CK(cudaMemcpyAsync(&niv, n_iv, 4, cudaMemcpyDeviceToHost, st));
@@ -535,11 +556,11 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
         if (s.h_offsets) cudaFreeHost(s.h_offsets);
         if (s.h_steps) cudaFreeHost(s.h_steps);
     }
-    DevBuf *all[] = {&mf->x, &mf->k64[0], &mf->k64[1], &mf->v32[0], &mf->v32[1], &mf->rank, &mf->ptr, &mf->best, &mf->aux0,
+    DevBuf *all[] = {&mf->x, &mf->k64[0], &mf->k64[1], &mf->v32[0], &mf->v32[1], &mf->rank, &mf->ptr, &mf->el[0], &mf->el[1], &mf->part, &mf->aux0,
                      &mf->aux1, &mf->tk[0], &mf->tk[1], &mf->tv[0], &mf->tv[1], &mf->tcount, &mf->keep, &mf->out_idx,
                      &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
                      &mf->sl_v[0], &mf->sl_v[1], &mf->sl_cnt, &mf->sl_off, &mf->hit_k[0], &mf->hit_k[1], &mf->hit_v[0],
-                     &mf->hit_v[1], &mf->hit_len, &mf->hit_count, &mf->iv, &mf->n_iv, &mf->scalars, &mf->tmpbuf};
+                     &mf->hit_v[1], &mf->hit_len, &mf->hit_count, &mf->iv, &mf->n_iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf};
     for (DevBuf *b : all) mf->release(*b);
 #ifndef NLZM_EMU
     if (mf->st) cudaStreamDestroy(mf->st);

@@ -31,6 +31,26 @@ typedef int64_t i64;
         k_##name<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n);                    \
         nlzm_launch_end(st);                                                            \
     }
+// One CTA of NT threads runs name##_cta(p, block, thread, smem); dynamic shared memory.
+#define NLZM_KERNEL_CTA(name, ParamsT, NT)                                              \
+    __global__ void __launch_bounds__(NT) k_##name(const ParamsT p) {                   \
+        extern __shared__ __align__(16) u8 nlzm_smem[];                                 \
+        name##_cta(p, blockIdx.x, threadIdx.x, nlzm_smem);                              \
+    }                                                                                   \
+    static inline int launch_##name(const ParamsT &p, u64 grid, size_t smem, cudaStream_t st) { \
+        if (grid == 0) return 0;                                                        \
+        static size_t configured = 0;                                                   \
+        if (smem > 48 * 1024 && smem > configured) {                                    \
+            cudaError_t e = cudaFuncSetAttribute(k_##name, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                        \
+            configured = smem;                                                          \
+        }                                                                               \
+        nlzm_launch_begin("k_" #name, st);                                              \
+        k_##name<<<(unsigned)grid, NT, smem, st>>>(p);                                  \
+        nlzm_launch_end(st);                                                            \
+        return (int)cudaGetLastError();                                                 \
+    }
+#define NLZM_CTA_SYNC() __syncthreads()
 DEV u32 nlzm_atomic_add(u32 *p, u32 v) { return atomicAdd(p, v); }
 DEV u64 nlzm_atomic_add64(unsigned long long *p, u64 v) { return atomicAdd(p, (unsigned long long)v); }
 DEV u32 nlzm_atomic_max(u32 *p, u32 v) { return atomicMax(p, v); }
@@ -61,9 +81,39 @@ typedef int cudaError_t;
         for (u64 i = 0; i < n; i++) name##_body(p, i);                                  \
         nlzm_launch_end(st);                                                            \
     }
-static inline u32 nlzm_atomic_add(u32 *p, u32 v) { u32 o = *p; *p += v; return o; }
-static inline u64 nlzm_atomic_add64(unsigned long long *p, u64 v) { u64 o = *p; *p += v; return o; }
-static inline u32 nlzm_atomic_max(u32 *p, u32 v) { u32 o = *p; if (v > o) *p = v; return o; }
+// CTA kernels run with real host threads and a barrier, so the atomics are real too
+#include <barrier>
+#include <thread>
+#include <vector>
+struct EmuCta { std::barrier<> *bar; };
+extern thread_local EmuCta nlzm_emu_cta;
+#define NLZM_CTA_SYNC() nlzm_emu_cta.bar->arrive_and_wait()
+#define NLZM_KERNEL_CTA(name, ParamsT, NT)                                              \
+    static inline int launch_##name(const ParamsT &p, u64 grid, size_t smem, cudaStream_t st) { \
+        if (grid == 0) return 0;                                                        \
+        nlzm_launch_begin("k_" #name, st);                                              \
+        std::vector<u8> sm(smem + 16);                                                  \
+        std::barrier<> bar(NT);                                                         \
+        std::vector<std::thread> th;                                                    \
+        for (u32 t = 0; t < NT; t++)                                                    \
+            th.emplace_back([&, t]() {                                                  \
+                nlzm_emu_cta.bar = &bar;                                                \
+                for (u64 b = 0; b < grid; b++) {                                        \
+                    name##_cta(p, (u32)b, t, sm.data());                                \
+                    bar.arrive_and_wait();                                              \
+                }                                                                       \
+            });                                                                         \
+        for (auto &x : th) x.join();                                                    \
+        nlzm_launch_end(st);                                                            \
+        return 0;                                                                       \
+    }
+static inline u32 nlzm_atomic_add(u32 *p, u32 v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline u64 nlzm_atomic_add64(unsigned long long *p, u64 v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline u32 nlzm_atomic_max(u32 *p, u32 v) {
+    u32 o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v > o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return o;
+}
 static inline int nlzm_ctz64(u64 v) { return __builtin_ctzll(v); }
 #endif
 

@@ -83,12 +83,22 @@ DEV void rk_lookup_body(const RkLookupParams &p, u64 t) {
 }
 NLZM_KERNEL_1D(rk_lookup, RkLookupParams)
 
-struct RkExtendParams { const u8 *x; Geom g; const u64 *hit_pos; const u32 *hit_dist; u32 *hit_len; };
+struct RkExtendParams {
+    const u8 *x; Geom g;
+    const u64 *hit_pos; const u32 *hit_dist; u32 *hit_len;
+    u64 *valid_pos; u32 *valid_idx; u32 *valid_count;     // hits that pass mlen >= match_min(dist), unsorted
+};
 DEV void rk_extend_body(const RkExtendParams &p, u64 i) {
     const u64 a = p.hit_pos[i];
     const u32 d = p.hit_dist[i];
     const u32 cap = geom_rem(p.g, a) & 0xFFFFu;          // uint16 max_len parameter, NLZM.cpp:759-760,1096-1097
-    p.hit_len[i] = lcp_cap(p.x, a - d, a, cap);
+    const u32 m = lcp_cap(p.x, a - d, a, cap);
+    p.hit_len[i] = m;
+    if (m >= match_min(d)) {                             // everything else is not a hit at all (NLZM.cpp:1099)
+        u32 j = nlzm_atomic_add(p.valid_count, 1u);
+        p.valid_pos[j] = a;
+        p.valid_idx[j] = (u32)i;
+    }
 }
 NLZM_KERNEL_1D(rk_extend, RkExtendParams)
 
@@ -96,8 +106,9 @@ struct RkInterval { u64 start; u32 dist; u32 len; u64 end; };
 
 struct RkChainParams {
     Geom g;
-    const u64 *hit_pos; const u32 *hit_dist; const u32 *hit_len;
-    const u32 *n_hits;
+    const u64 *valid_pos; const u32 *valid_idx;          // valid hits sorted by position
+    const u32 *hit_dist; const u32 *hit_len;             // indexed by raw hit index
+    const u32 *n_valid;
     RkInterval *iv; u32 *n_iv;
 };
 
@@ -117,13 +128,13 @@ HD u64 rk_carry_end(const Geom &g, u64 ca, u32 cl) {
 
 // The sequential part: one thread walks the position-sorted hits.
 DEV void rk_chain_body(const RkChainParams &p, u64) {
-    const u32 n = *p.n_hits;
+    const u32 n = *p.n_valid;
     u32 cl = 0, cd = 0, cep = 0, niv = 0;
     u64 ca = 0;
     for (u32 i = 0; i < n; i++) {
-        const u64 a = p.hit_pos[i];
-        const u32 d = p.hit_dist[i], m = p.hit_len[i];
-        if (m < match_min(d)) continue;                                   // not a hit at all (NLZM.cpp:1099)
+        const u64 a = p.valid_pos[i];
+        const u32 ri = p.valid_idx[i];
+        const u32 d = p.hit_dist[ri], m = p.hit_len[ri];
         const bool alive = cl > 0 && geom_epoch(p.g, a) == cep && a - ca < cl;
         if (alive && cl >= NLZM_RK_BLOCK) continue;                       // no lookups under a long carry (1090)
         if (alive && m < cl) continue;                                    // must be >= the carry's original length (1099)

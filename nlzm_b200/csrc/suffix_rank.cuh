@@ -34,6 +34,3 @@ DEV void rank_pair_body(const RankPairParams &p, u64 i) {
 }
 NLZM_KERNEL_1D(rank_pair, RankPairParams)
 
-struct RankElemParams { const u32 *rank; u64 *elem; };
-DEV void rank_elem_body(const RankElemParams &p, u64 i) { p.elem[i] = ((u64)p.rank[i] << 32) | (u32)i; }
-NLZM_KERNEL_1D(rank_elem, RankElemParams)
