@@ -145,7 +145,17 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL may print its version banner on stdout; the contract is ONE JSON line there
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     total = args.bytes_per_gpu * world
     # input: generated once on rank 0, replicated into every GPU's HBM (setup, not the hot path)
@@ -233,12 +243,12 @@ def run_ours(args):
     barrier()
 
     t = torch.tensor([dev_ms, wall_ms, e2e_ms], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([n_steps, n_tuples, launches], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([n_steps, n_tuples, launches, d2h_bytes], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms, e2e_ms = [float(v) for v in t.tolist()]
-    all_steps, all_tuples, all_launches = [int(v) for v in cnt.tolist()]
+    all_steps, all_tuples, all_launches, d2h_bytes = [int(v) for v in cnt.tolist()]
 
     if rank == 0:
         ms_per_step = dev_ms / args.steps

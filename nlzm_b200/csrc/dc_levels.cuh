@@ -21,10 +21,21 @@
 #pragma once
 #include "common.cuh"
 
+#if defined(NLZM_EMU) && defined(NLZM_EMU_STATS)
+extern unsigned long long nlzm_stats[16];
+#define NLZM_STAT(i, v) __atomic_fetch_add(&nlzm_stats[i], (unsigned long long)(v), __ATOMIC_RELAXED)
+#else
+#define NLZM_STAT(i, v) ((void)0)
+#endif
+
 struct PtrEntry {
     u64 pg;   // key (rank<<32|pos) of the nearest element to the rank-left with a greater position in
               // the same segment, 0 if none
     u64 ng;   // same to the rank-right, ~0 if none
+    u16 lpg;  // lcp(this, pg) capped at 264 (0 if none): lcp(a, pg) = min(lcp(a, this), lpg) along a chain
+    u16 lng;  // lcp(this, ng)
+    u32 pad0;
+    u64 pad1; // 32 bytes = one sector per entry
 };
 #define NLZM_PG_NONE 0ull
 #define NLZM_NG_NONE 0xFFFFFFFFFFFFFFFFull
@@ -34,9 +45,14 @@ struct Elem {
     u64 key;    // rank << 32 | universe-relative position: strict total order of the suffixes
     u64 p0;     // text bytes 0..7 of the suffix (little endian: byte 0 in the low bits)
     u64 p1;     // text bytes 8..15
-    u64 tail;   // text bytes 16..21 in bits 0..47, best match length so far in bits 48..63
+    u64 tail;   // bits 0..15 text bytes 16..17 | 16..31 best length so far | 32..47 lpg | 48..63 lng
 };
-#define NLZM_ELEM_PREFIX 22u
+#define NLZM_ELEM_PREFIX 18u
+HD u32 elem_best(u64 tail) { return (u32)(tail >> 16) & 0xFFFFu; }
+HD u32 elem_lpg(u64 tail) { return (u32)(tail >> 32) & 0xFFFFu; }
+HD u32 elem_lng(u64 tail) { return (u32)(tail >> 48); }
+HD u64 elem_tail(u32 b1617, u32 best, u32 lpg, u32 lng) { return (u64)b1617 | ((u64)best << 16) | ((u64)lpg << 32) | ((u64)lng << 48); }
+HD u64 elem_set_best(u64 tail, u32 best) { return (tail & ~0xFFFF0000ull) | ((u64)best << 16); }
 
 struct TupleSink {
     u64 *keys;       // (a_rel << 9) | len
@@ -288,6 +304,34 @@ DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         NLZM_CTA_SYNC();
         cur ^= 1;
     }
+    // link lcps of the final pointers (reuse best/cor storage is not possible: keep them in registers via smem cor/arr[cur^1])
+    u16 *LPG = s.arr[cur ^ 1];      // the other level array is free now
+    u16 *LNG = s.cor;
+    for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
+        const u32 g0 = s.pg[i], g1 = s.ng[i];
+        u32 l0 = 0, l1 = 0;
+        if (g0 != NLZM_L16_NONE && s.k4[g0] == s.k4[i]) {
+            const u64 later = abs0 + (g0 > i ? g0 : i);
+            const u32 lim = (p.g.flen - later) < NLZM_MATCH_MAX ? (u32)(p.g.flen - later) : NLZM_MATCH_MAX;
+            l0 = 4; while (l0 < lim && s.text[g0 + l0] == s.text[i + l0]) ++l0;
+            if (l0 > lim) l0 = lim;
+        } else if (g0 != NLZM_L16_NONE) {
+            const u32 d = s.k4[g0] ^ s.k4[i];
+            l0 = (u32)nlzm_ctz64((u64)d | (1ull << 32)) >> 3;
+        }
+        if (g1 != NLZM_L16_NONE && s.k4[g1] == s.k4[i]) {
+            const u64 later = abs0 + (g1 > i ? g1 : i);
+            const u32 lim = (p.g.flen - later) < NLZM_MATCH_MAX ? (u32)(p.g.flen - later) : NLZM_MATCH_MAX;
+            l1 = 4; while (l1 < lim && s.text[g1 + l1] == s.text[i + l1]) ++l1;
+            if (l1 > lim) l1 = lim;
+        } else if (g1 != NLZM_L16_NONE) {
+            const u32 d = s.k4[g1] ^ s.k4[i];
+            l1 = (u32)nlzm_ctz64((u64)d | (1ull << 32)) >> 3;
+        }
+        LPG[i] = (u16)l0;
+        LNG[i] = (u16)l1;
+    }
+    NLZM_CTA_SYNC();
     // hand over to the merge levels: fat elements in rank order, pointers by position
     const u16 *A = s.arr[cur];
     for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
@@ -295,18 +339,17 @@ DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         const u8 *t = s.text + pos;
         Elem e;
         e.key = ((u64)s.rnk[pos] << 32) | (t0 + pos);
-        u64 a = 0, b = 0, c = 0;
+        u64 a = 0, b = 0;
         #pragma unroll
         for (int k = 0; k < 8; k++) { a |= (u64)t[k] << (8 * k); b |= (u64)t[8 + k] << (8 * k); }
-        #pragma unroll
-        for (int k = 0; k < 6; k++) c |= (u64)t[16 + k] << (8 * k);
         e.p0 = a; e.p1 = b;
-        e.tail = c | ((u64)s.best[pos] << 48);
+        e.tail = elem_tail((u32)t[16] | ((u32)t[17] << 8), s.best[pos], LPG[pos], LNG[pos]);
         p.nxt[t0 + i] = e;
         PtrEntry pe;
         const u32 g0 = s.pg[i], g1 = s.ng[i];
         pe.pg = g0 == NLZM_L16_NONE ? NLZM_PG_NONE : (((u64)s.rnk[g0] << 32) | (t0 + g0));
         pe.ng = g1 == NLZM_L16_NONE ? NLZM_NG_NONE : (((u64)s.rnk[g1] << 32) | (t0 + g1));
+        pe.lpg = LPG[i]; pe.lng = LNG[i]; pe.pad0 = 0; pe.pad1 = 0;
         p.ptr[t0 + i] = pe;
     }
 }
@@ -357,48 +400,46 @@ DEV u32 elem_prefix_lcp(const Elem &a, const Elem &b) {
     if (d) return (u32)nlzm_ctz64(d) >> 3;
     d = a.p1 ^ b.p1;
     if (d) return 8 + ((u32)nlzm_ctz64(d) >> 3);
-    d = (a.tail ^ b.tail) & 0xFFFFFFFFFFFFull;
+    d = (a.tail ^ b.tail) & 0xFFFFull;
     if (d) return 16 + ((u32)nlzm_ctz64(d) >> 3);
     return NLZM_ELEM_PREFIX;
 }
 
-// lcp of text at c_abs with the suffix of element a (prefix in registers), capped at lim
-DEV u32 elem_text_lcp(const DcParams &p, const Elem &a, u64 a_abs, u64 c_abs, u32 lim) {
-    u32 m;
-    u64 d = load8(p.x, c_abs) ^ a.p0;
-    if (d) m = (u32)nlzm_ctz64(d) >> 3;
-    else {
-        d = load8(p.x, c_abs + 8) ^ a.p1;
-        if (d) m = 8 + ((u32)nlzm_ctz64(d) >> 3);
-        else {
-            d = (load8(p.x, c_abs + 16) ^ a.tail) & 0xFFFFFFFFFFFFull;
-            if (d) m = 16 + ((u32)nlzm_ctz64(d) >> 3);
-            else m = lim > NLZM_ELEM_PREFIX ? NLZM_ELEM_PREFIX + lcp_cap(p.x, c_abs + NLZM_ELEM_PREFIX, a_abs + NLZM_ELEM_PREFIX, lim - NLZM_ELEM_PREFIX) : NLZM_ELEM_PREFIX;
-        }
-    }
-    return m < lim ? m : lim;
+// full lcp of the suffixes behind two elements (prefixes first, text beyond), capped at lim
+DEV u32 elem_pair_lcp(const DcParams &p, const Elem &a, const Elem &b, u32 lim) {
+    u32 l = elem_prefix_lcp(a, b);
+    if (l >= NLZM_ELEM_PREFIX && lim > NLZM_ELEM_PREFIX)
+        l = NLZM_ELEM_PREFIX + lcp_cap(p.x, p.u0 + (u32)a.key + NLZM_ELEM_PREFIX, p.u0 + (u32)b.key + NLZM_ELEM_PREFIX, lim - NLZM_ELEM_PREFIX);
+    return l < lim ? l : lim;
 }
 
-// Walk one greater-position chain of the left half; the first element is a neighbour whose element
-// (with prefix) is at hand, the following ones are reached through ptr[] and compared against text.
+// Walk one greater-position chain of the left half. The first element is a rank neighbour whose element
+// (prefix, link lcp) sits in shared memory; the lcp with every further chain element follows from the
+// link lcps stored with the pointers: lcp(a, pg(c)) = min(lcp(a, c), lcp(c, pg(c))). One 32-byte ptr[]
+// read per hop, none at all when the chain ends at the neighbour.
 DEV void dc_walk(const DcParams &p, const Elem &ea, u64 a_abs, u32 cap, u32 best_in, const Elem *first, bool left, u32 &new_best) {
     if (!first) return;
     const u32 a_rel = (u32)ea.key;
     u32 c = (u32)first->key;
-    u32 l = elem_prefix_lcp(ea, *first);
-    if (l >= NLZM_ELEM_PREFIX && cap > NLZM_ELEM_PREFIX)
-        l = NLZM_ELEM_PREFIX + lcp_cap(p.x, p.u0 + c + NLZM_ELEM_PREFIX, a_abs + NLZM_ELEM_PREFIX, cap - NLZM_ELEM_PREFIX);
-    if (l > cap) l = cap;
+    u32 l = elem_pair_lcp(p, ea, *first, cap);
+    u32 link = left ? elem_lpg(first->tail) : elem_lng(first->tail);
+    bool have_entry = false;
+    PtrEntry en;
     u32 pend_len = 0, pend_c = 0;
-    while (true) {
-        if (l <= best_in) break;
+    while (l > best_in) {
         if (pend_len && l < pend_len) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
-        pend_len = l; pend_c = c;
+        pend_len = l; pend_c = c;                              // equal lcp: the nearer element replaces the farther one
         if (l > new_best) new_best = l;
-        const u64 k = left ? p.ptr[c].pg : p.ptr[c].ng;
+        const u32 l_next = l < link ? l : link;                // lcp never grows along the chain
+        if (l_next <= best_in) break;                          // the chain ends here without touching memory
+        if (!have_entry) en = p.ptr[c];                        // the neighbour's pointer (its link lcp came with the element)
+        const u64 k = left ? en.pg : en.ng;
         if (k == (left ? NLZM_PG_NONE : NLZM_NG_NONE)) break;
         c = (u32)k;
-        l = elem_text_lcp(p, ea, a_abs, p.u0 + c, l);        // lcp never grows along the chain
+        l = l_next;
+        en = p.ptr[c];
+        have_entry = true;
+        link = left ? en.lpg : en.lng;
     }
     if (pend_len) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
 }
@@ -475,13 +516,14 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         const u32 pos = (u32)e.key;
         const u64 a_abs = p.u0 + pos;
         u32 cap;
-        const u32 best_in = (u32)(e.tail >> 48);
+        const u32 best_in = elem_best(e.tail);
         if (!dc_query_cap(p, a_abs, cap) || best_in >= cap || pos - (s.r_beg - 1) > p.g.W - 1) continue;
         const u32 li = lcnt[o];
+        NLZM_STAT(0, 1);
         bool want = false;
         if (l0 + li > 0) { u32 l = elem_prefix_lcp(e, el[li]); l = l < cap ? l : cap; want |= (l > best_in) || (l >= NLZM_ELEM_PREFIX && cap > NLZM_ELEM_PREFIX); }
         if (l0 + li < s.l_len) { u32 l = elem_prefix_lcp(e, el[li + 1]); l = l < cap ? l : cap; want |= (l > best_in) || (l >= NLZM_ELEM_PREFIX && cap > NLZM_ELEM_PREFIX); }
-        if (want) act[nlzm_atomic_add(act_n, 1u)] = (u16)o;
+        if (want) { NLZM_STAT(1, 1); act[nlzm_atomic_add(act_n, 1u)] = (u16)o; }
     }
     NLZM_CTA_SYNC();
 
@@ -495,12 +537,12 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         const u64 a_abs = p.u0 + pos;
         u32 cap = 0;
         dc_query_cap(p, a_abs, cap);
-        const u32 best_in = (u32)(ea.tail >> 48);
+        const u32 best_in = elem_best(ea.tail);
         const u32 li = lcnt[o];
         u32 nb = best_in;
         dc_walk(p, ea, a_abs, cap, best_in, (l0 + li > 0) ? &el[li] : nullptr, true, nb);
         dc_walk(p, ea, a_abs, cap, best_in, (l0 + li < s.l_len) ? &el[li + 1] : nullptr, false, nb);
-        if (nb != best_in) e.tail = (ea.tail & 0xFFFFFFFFFFFFull) | ((u64)nb << 48);
+        if (nb != best_in) e.tail = elem_set_best(ea.tail, nb);
     }
     NLZM_CTA_SYNC();
 
@@ -521,12 +563,33 @@ DEV void dc_link_body(const DcParams &p, u64 idx64) {
     const u32 idx = (u32)idx64;
     const SegGeom s = seg_geom(p.n, p.h, idx);
     if (idx >= s.r_beg || s.r_len == 0) return;
-    const u32 pos = (u32)p.cur[idx].key;
+    const Elem e = p.cur[idx];
+    const u32 pos = (u32)e.key;
     const u32 u = p.corank[idx];
-    PtrEntry e = p.ptr[pos];
+    PtrEntry en = p.ptr[pos];
     bool ch = false;
-    if (u > 0) { const u64 k = p.cur[s.r_beg + u - 1].key; if (k > e.pg) { e.pg = k; ch = true; } }
-    if (u < s.r_len) { const u64 k = p.cur[s.r_beg + u].key; if (k < e.ng) { e.ng = k; ch = true; } }
-    if (ch) p.ptr[pos] = e;
+    if (u > 0) {
+        const Elem r = p.cur[s.r_beg + u - 1];
+        if (r.key > en.pg) {
+            const u64 left_in_file = p.g.flen - (p.u0 + (u32)r.key);          // r is the later position
+            en.pg = r.key;
+            en.lpg = (u16)elem_pair_lcp(p, e, r, left_in_file < NLZM_MATCH_MAX ? (u32)left_in_file : NLZM_MATCH_MAX);
+            ch = true;
+        }
+    }
+    if (u < s.r_len) {
+        const Elem r = p.cur[s.r_beg + u];
+        if (r.key < en.ng) {
+            const u64 left_in_file = p.g.flen - (p.u0 + (u32)r.key);
+            en.ng = r.key;
+            en.lng = (u16)elem_pair_lcp(p, e, r, left_in_file < NLZM_MATCH_MAX ? (u32)left_in_file : NLZM_MATCH_MAX);
+            ch = true;
+        }
+    }
+    if (ch) {
+        p.ptr[pos] = en;
+        // the merged copy of this element (already written by k_dc_merge_tile) carries the link lcps too
+        p.nxt[idx + u].tail = elem_tail((u32)e.tail & 0xFFFFu, elem_best(e.tail), en.lpg, en.lng);
+    }
 }
 NLZM_KERNEL_1D(dc_link, DcParams)

@@ -25,6 +25,10 @@
 
 #ifdef NLZM_EMU
 thread_local EmuCta nlzm_emu_cta;
+#ifdef NLZM_EMU_STATS
+unsigned long long nlzm_stats[16];
+extern "C" unsigned long long *nlzm_emu_stats() { return nlzm_stats; }
+#endif
 #endif
 
 // ---- launch accounting / per-kernel timing ----------------------------------------------------
