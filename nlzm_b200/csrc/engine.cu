@@ -199,31 +199,50 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
     cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&ev2);
     cudaEventRecord(ev0, st);
 
-    // --- S: prefix doubling 8 -> 16 -> ... -> >= 264 bytes
-    RankInitParams ip{x.as<u8>(), u0, k64[0].as<u64>(), v32[0].as<u32>()};
-    launch_rank_init(ip, n, st);
-    u64 depth = 8;
+    // --- S: prefix doubling 8 -> 16 -> ... -> >= 264 bytes; rounds after the first only re-sort the
+    //        positions whose group is still ambiguous. Scratch comes out of the (not yet used) level arrays.
+    CKI(ensure(el[0], n * sizeof(Elem))); CKI(ensure(el[1], n * sizeof(Elem)));
+    u32 *scratch = el[1].as<u32>();
+    u32 *new_grp = scratch, *act_flag = scratch + n, *act_idx = scratch + 2 * n;
+    u32 *grp_buf[2] = {scratch + 3 * n, scratch + 4 * n}, *pos_buf[2] = {scratch + 5 * n, scratch + 6 * n};
+    const u32 nb = bits_for(n + 2);
+    {
+        RankInitParams ip{x.as<u8>(), u0, k64[0].as<u64>(), v32[0].as<u32>()};
+        launch_rank_init(ip, n, st);
+    }
+    u64 m = n, depth = 8;
+    int ab = 0;
+    bool round0 = true;
     while (true) {
         int sel = 0;
-        CKI(prim_sort_pairs64(tmp, k64[0].as<u64>(), k64[1].as<u64>(), v32[0].as<u32>(), v32[1].as<u32>(), n, 0, 64, st, &sel));
-        RankHeadParams hp{k64[sel].as<u64>(), aux0.as<u32>(), aux1.as<u32>()};
-        launch_rank_head(hp, n, st);
-        CKI(prim_sum(tmp, aux1.as<u32>(), sum_dev, n, st));
-        CKI(prim_inclusive_max(tmp, aux0.as<u32>(), aux0.as<u32>(), n, st));
-        RankScatterParams sp{v32[sel].as<u32>(), aux0.as<u32>(), rank.as<u32>()};
-        launch_rank_scatter(sp, n, st);
-        u64 groups = 0;
-        CK(cudaMemcpyAsync(&groups, sum_dev, 8, cudaMemcpyDeviceToHost, st));
+        CKI(prim_sort_pairs64(tmp, k64[0].as<u64>(), k64[1].as<u64>(), v32[0].as<u32>(), v32[1].as<u32>(), m, 0,
+                              round0 ? 64 : (int)(2 * nb), st, &sel));
+        RankHeadParams hp{k64[sel].as<u64>(), aux0.as<u32>(), aux1.as<u32>(), nb, round0 ? 1u : 0u};
+        launch_rank_head(hp, m, st);
+        CKI(prim_inclusive_max(tmp, aux0.as<u32>(), aux0.as<u32>(), m, st));
+        CKI(prim_inclusive_max(tmp, aux1.as<u32>(), aux1.as<u32>(), m, st));
+        RankAssignParams ap{k64[sel].as<u64>(), v32[sel].as<u32>(), aux0.as<u32>(), aux1.as<u32>(), rank.as<u32>(),
+                            new_grp, act_flag, m, nb, round0 ? 1u : 0u};
+        launch_rank_assign(ap, m, st);
+        depth *= 2;                                       // ranks now order the first `depth` bytes
+        if (depth / 2 >= NLZM_MATCH_MAX) break;
+        CKI(prim_sum(tmp, act_flag, sum_dev, m, st));
+        u64 m_next = 0;
+        CK(cudaMemcpyAsync(&m_next, sum_dev, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        if (depth >= NLZM_MATCH_MAX || groups == n) break;
-        RankPairParams pp{rank.as<u32>(), k64[0].as<u64>(), v32[0].as<u32>(), n, depth};
-        launch_rank_pair(pp, n, st);
-        depth *= 2;
+        if (m_next == 0) break;
+        CKI(prim_exclusive_sum(tmp, act_flag, act_idx, m, st));
+        RankCompactParams cp{act_flag, act_idx, new_grp, v32[sel].as<u32>(), grp_buf[ab], pos_buf[ab]};
+        launch_rank_compact(cp, m, st);
+        m = m_next;
+        RankKeysParams kp{grp_buf[ab], pos_buf[ab], rank.as<u32>(), k64[0].as<u64>(), v32[0].as<u32>(), n, depth / 2, nb};
+        launch_rank_keys(kp, m, st);
+        ab ^= 1;
+        round0 = false;
     }
     cudaEventRecord(ev1, st);
 
     // --- T: first NLZM_BASE_LOG levels in shared memory, then one merge-path pass per level
-    CKI(ensure(el[0], n * sizeof(Elem))); CKI(ensure(el[1], n * sizeof(Elem)));
     const u64 tiles = (n + NLZM_MT_TILE - 1) / NLZM_MT_TILE;
     CKI(ensure(part, (tiles + 2) * 4));
     DcParams dp;
