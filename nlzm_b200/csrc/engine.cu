@@ -118,6 +118,7 @@ struct nlzm_mf {
     PrimTemp tmp;
     DevBuf tmpbuf;
     u32 tuple_cap_mult = 6;
+    bool rk_all_hits = false, rk_overflowed = false;
 
     Slot slot[2];
     std::mutex mu;
@@ -287,7 +288,7 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
             launch_bt_bucket(bp, m, st);
             int sel = 0;
             CKI(prim_sort_pairs32(tmp, e_k[0].as<u32>(), e_k[1].as<u32>(), e_v[0].as<u32>(), e_v[1].as<u32>(), m, 0, (int)g.bt_bits, st, &sel));
-            HtInvParams vp{e_v[sel].as<u32>(), e_inv.as<u32>()};
+            HtInvParams vp{e_v[sel].as<u32>(), e_inv.as<u32>(), 0u};
             launch_ht_inv(vp, m, st);
             BtShortParams sp{x.as<u8>(), g, e_k[sel].as<u32>(), e_v[sel].as<u32>(), e_inv.as<u32>(), s0, own_b, sink()};
             launch_bt_short(sp, pe - own_b, st);
@@ -311,15 +312,16 @@ int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     const u64 m = pe * c.rows;                                       // events of the whole prefix (tables never age)
     CKI(ensure(e_k[0], m * 4)); CKI(ensure(e_k[1], m * 4));
     CKI(ensure(e_v[0], m * 4)); CKI(ensure(e_v[1], m * 4));
-    CKI(ensure(e_inv, m * 4));
+    const u64 first_ev = own_b * c.rows;
+    CKI(ensure(e_inv, (m - first_ev) * 4));
     CKI(ensure_prim(m));
     HtEventParams ep{x.as<u8>(), c, e_k[0].as<u32>(), e_v[0].as<u32>()};
     launch_ht_event(ep, pe, st);
     int sel = 0;
     CKI(prim_sort_pairs32(tmp, e_k[0].as<u32>(), e_k[1].as<u32>(), e_v[0].as<u32>(), e_v[1].as<u32>(), m, 0, (int)c.bits + 1, st, &sel));
-    HtInvParams vp{e_v[sel].as<u32>(), e_inv.as<u32>()};
+    HtInvParams vp{e_v[sel].as<u32>(), e_inv.as<u32>(), (u32)first_ev};
     launch_ht_inv(vp, m, st);
-    HtFindParams fp{x.as<u8>(), g, c, e_k[sel].as<u32>(), e_v[sel].as<u32>(), e_inv.as<u32>(), own_b, sink()};
+    HtFindParams fp{x.as<u8>(), g, c, e_k[sel].as<u32>(), e_v[sel].as<u32>(), e_inv.as<u32>(), (u32)first_ev, (u32)m, own_b, sink()};
     launch_ht_find(fp, pe - own_b, st);
     return 0;
 }
@@ -345,7 +347,7 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     CKI(ensure(sl_v[0], n_blk * 4)); CKI(ensure(sl_v[1], n_blk * 4));
     CKI(ensure(sl_cnt, (n_slots + 1) * 4)); CKI(ensure(sl_off, (n_slots + 1) * 4));
     const u64 range = rk_e - rk_b;
-    u64 hit_cap = range / 4 + (1u << 20);
+    u64 hit_cap = rk_all_hits ? range + 1024 : range / 4 + (1u << 20);
     CKI(ensure(hit_k[0], hit_cap * 8)); CKI(ensure(hit_k[1], hit_cap * 8));
     CKI(ensure(hit_v[0], hit_cap * 4)); CKI(ensure(hit_v[1], hit_cap * 4));
     CKI(ensure(hit_len, hit_cap * 4));
@@ -371,7 +373,11 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     u32 n_hits = 0;
     CK(cudaMemcpyAsync(&n_hits, hit_count, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (n_hits > hit_cap) return fail(NLZM_MF_E_OVERFLOW, "RK raw-hit buffer overflow");
+    if (n_hits > hit_cap) {                      // dense hits (e.g. zero runs): redo with room for one hit per position
+        rk_all_hits = true;
+        rk_overflowed = true;
+        return fail(NLZM_MF_E_OVERFLOW, "RK raw-hit buffer overflow");
+    }
     if (n_hits == 0) return 0;
     // extension of every raw hit (any order); the few that are real hits are compacted, sorted by
     // position and fed to the sequential carry state machine
@@ -479,7 +485,7 @@ int nlzm_mf::find_impl(u64 b, u64 e, int si, bool to_host) {
         }
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); cudaEventDestroy(e4);
         if (r == NLZM_MF_E_OVERFLOW && attempt < 3) {      // rare: dense candidates; grow and redo the range
-            tuple_cap_mult *= 2;
+            if (rk_overflowed) rk_overflowed = false; else tuple_cap_mult *= 2;
             continue;
         }
         if (r) return r;

@@ -33,8 +33,13 @@ DEV void ht_event_body(const HtEventParams &p, u64 a) {
 }
 NLZM_KERNEL_1D(ht_event, HtEventParams)
 
-struct HtInvParams { const u32 *vals; u32 *inv; };
-DEV void ht_inv_body(const HtInvParams &p, u64 j) { p.inv[p.vals[j]] = (u32)j; }
+// inverse permutation, only for events at or after `first_ev` (the range being answered): tables
+// never age, so the sorted event list covers the whole prefix, but only own events start a lookup
+struct HtInvParams { const u32 *vals; u32 *inv; u32 first_ev; };
+DEV void ht_inv_body(const HtInvParams &p, u64 j) {
+    const u32 v = p.vals[j];
+    if (v >= p.first_ev) p.inv[v - p.first_ev] = (u32)j;
+}
 NLZM_KERNEL_1D(ht_inv, HtInvParams)
 
 struct HtFindParams {
@@ -43,15 +48,30 @@ struct HtFindParams {
     HtCfg c;
     const u32 *skeys;    // sorted cells
     const u32 *svals;    // event ids in (cell, time) order
-    const u32 *inv;      // event id -> index in the sorted arrays
+    const u32 *inv;      // event id - first_ev -> index in the sorted arrays
+    u32 first_ev;        // first event id covered by inv
+    u32 n_ev;            // number of sorted events
     u64 own_b;
     TupleSink sink;
 };
 
+// index of event `ev` (which writes `cell`) in the sorted arrays
+DEV u32 ht_event_index(const HtFindParams &p, u32 ev, u32 cell) {
+    if (ev >= p.first_ev) return p.inv[ev - p.first_ev];
+    // an event before the answered range (rare: a chain that reaches back): binary search by (cell, id)
+    u32 lo = 0, hi = p.n_ev;
+    while (lo < hi) {
+        const u32 mid = lo + ((hi - lo) >> 1);
+        const u32 c = p.skeys[mid];
+        if (c < cell || (c == cell && p.svals[mid] < ev)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // raw u32 content of the cell that event `ev` (of the access at time t) is about to overwrite
-DEV u32 ht_cell_before(const HtFindParams &p, u32 ev, u64 t) {
+DEV u32 ht_cell_before(const HtFindParams &p, u32 ev, u64 t, u32 cell0) {
     const u32 cmask = (1u << (32 - p.g.hb)) - 1;
-    u32 j = p.inv[ev];
+    u32 j = ht_event_index(p, ev, cell0);
     while (true) {
         if (j == 0) return NLZM_NONE32;
         const u32 cell = p.skeys[j];
@@ -66,7 +86,7 @@ DEV u32 ht_cell_before(const HtFindParams &p, u32 ev, u64 t) {
         }
         // the writer pushed the old content of its own bucket cell (cell - 1) here
         t = w;
-        j = p.inv[(u32)w * p.c.rows];
+        j = ht_event_index(p, (u32)w * p.c.rows, cell - 1);
     }
 }
 
@@ -81,7 +101,7 @@ DEV void ht_find_body(const HtFindParams &p, u64 i) {
     const u64 base = a - P;
     u32 best = 1;                                                     // MATCH_MIN - 1, NLZM.cpp:917
     for (u32 r = 0; r < p.c.rows; r++) {
-        const u32 row = ht_cell_before(p, (u32)a * p.c.rows + r, a);
+        const u32 row = ht_cell_before(p, (u32)a * p.c.rows + r, a, (hash >> (32 - p.c.bits)) + r);
         if (best < cap && (row >> p.g.hb) == chk) {
             const u32 sp = row & (p.g.W - 1);
             if (sp < P && P - sp <= p.g.W - 1) {

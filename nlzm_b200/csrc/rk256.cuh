@@ -60,16 +60,18 @@ DEV void rk_lookup_body(const RkLookupParams &p, u64 t) {
     for (;; ) {
         const u32 slot = h >> shift;
         // last block of this slot that starts before a (the insert at a itself comes after the lookup)
+        // (binary search: a slot can hold very many blocks, e.g. every block of a zero run)
         u32 lo = p.slot_off[slot], hi = p.slot_off[slot + 1];
         u32 e = NLZM_NONE32;
-        while (hi > lo) {
-            u32 j = p.slot_blk[hi - 1];
-            if ((u64)j * NLZM_RK_BLOCK < a) {
-                u64 s = (u64)j * NLZM_RK_BLOCK;
-                e = geom_P(p.g, s) | (p.hblk[j] << p.g.hb);      // NLZM.cpp:1111: full P, spills into the check bits
-                break;
-            }
-            --hi;
+        const u32 first = lo;
+        while (lo < hi) {                                        // first list entry whose block starts at or after a
+            const u32 mid = lo + ((hi - lo) >> 1);
+            if ((u64)p.slot_blk[mid] * NLZM_RK_BLOCK < a) lo = mid + 1; else hi = mid;
+        }
+        if (lo > first) {
+            const u32 j = p.slot_blk[lo - 1];
+            const u64 s = (u64)j * NLZM_RK_BLOCK;
+            e = geom_P(p.g, s) | (p.hblk[j] << p.g.hb);          // NLZM.cpp:1111: full P, spills into the check bits
         }
         const u32 P = geom_P(p.g, a);
         const u32 sp = e & (p.g.W - 1);
@@ -131,19 +133,28 @@ DEV void rk_chain_body(const RkChainParams &p, u64) {
     const u32 n = *p.n_valid;
     u32 cl = 0, cd = 0, cep = 0, niv = 0;
     u64 ca = 0;
-    for (u32 i = 0; i < n; i++) {
+    u32 i = 0;
+    while (i < n) {
         const u64 a = p.valid_pos[i];
         const u32 ri = p.valid_idx[i];
         const u32 d = p.hit_dist[ri], m = p.hit_len[ri];
         const bool alive = cl > 0 && geom_epoch(p.g, a) == cep && a - ca < cl;
-        if (alive && cl >= NLZM_RK_BLOCK) continue;                       // no lookups under a long carry (1090)
-        if (alive && m < cl) continue;                                    // must be >= the carry's original length (1099)
+        if (alive && cl >= NLZM_RK_BLOCK) {
+            // no lookups under a long carry (NLZM.cpp:1090): skip straight to the first hit at or after its end
+            const u64 end = rk_carry_end(p.g, ca, cl);
+            u32 lo = i + 1, hi = n;
+            while (lo < hi) { const u32 mid = lo + ((hi - lo) >> 1); if (p.valid_pos[mid] < end) lo = mid + 1; else hi = mid; }
+            i = lo;
+            continue;
+        }
+        if (alive && m < cl) { ++i; continue; }                           // must be >= the carry's original length (1099)
         if (cl > 0) {
             u64 end = rk_carry_end(p.g, ca, cl);
             RkInterval v; v.start = ca; v.dist = cd; v.len = cl; v.end = (a + 1 < end) ? a + 1 : end;   // (A) still fires at a
             p.iv[niv++] = v;
         }
         ca = a; cd = d; cl = m; cep = geom_epoch(p.g, a);
+        ++i;
     }
     if (cl > 0) {
         RkInterval v; v.start = ca; v.dist = cd; v.len = cl; v.end = rk_carry_end(p.g, ca, cl);

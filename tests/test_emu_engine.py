@@ -22,9 +22,9 @@ def _run(lib, x, hb, mask=15, cuts=None):
         return np.concatenate(offs), np.concatenate(ds), np.concatenate(ls)
 
 
-@pytest.mark.parametrize("kind,n,hb", [("text", 250_000, 24), ("text", 200_000, 15), ("longrange", 350_000, 24),
-                                       ("longrange", 300_000, 16), ("mixed", 250_000, 16), ("zeros", 60_000, 15),
-                                       ("random", 100_000, 20)])
+@pytest.mark.parametrize("kind,n,hb", [("text", 90_000, 24), ("text", 120_000, 15), ("longrange", 140_000, 24),
+                                       ("longrange", 110_000, 16), ("mixed", 100_000, 16), ("zeros", 30_000, 15),
+                                       ("random", 50_000, 20)])
 def test_emu_all_finders(emu_lib, orc, kind, n, hb):
     from nlzm_b200 import synth
     x = synth.make(kind, n)
@@ -36,7 +36,7 @@ def test_emu_all_finders(emu_lib, orc, kind, n, hb):
 @pytest.mark.parametrize("mask", [1, 2, 4, 8])
 def test_emu_each_finder(emu_lib, orc, mask):
     from nlzm_b200 import synth
-    x = np.concatenate([synth.text(100_000, 21), synth.longrange(200_000, 22), synth.mixed(80_000, 23)])
+    x = np.concatenate([synth.text(40_000, 21), synth.longrange(70_000, 22), synth.mixed(30_000, 23)])
     ref = orc.find(x, 15, mask)
     got = _run(emu_lib, x, 15, mask)
     assert orc.csr_equal(ref, got), orc.first_diff(ref, got)
@@ -44,7 +44,7 @@ def test_emu_each_finder(emu_lib, orc, mask):
 
 def test_emu_block_mode(emu_lib, orc):
     from nlzm_b200 import synth
-    x = synth.longrange(300_000, 31)
+    x = synth.longrange(110_000, 31)
     n = x.size
     for hb in (15, 24):
         ref = orc.find(x, hb, orc.F_ALL)

@@ -34,13 +34,13 @@ def _need(path):
         pytest.skip(f"{os.path.relpath(path, ROOT)} not built (make -C oracle gpu, needs /root/reference)")
 
 
-@pytest.mark.parametrize("kind,n,hb", [("text", 400_000, 24), ("longrange", 500_000, 15), ("mixed", 300_000, 20)])
+@pytest.mark.parametrize("kind,n,hb", [("text", 150_000, 24), ("longrange", 200_000, 15), ("mixed", 120_000, 20)])
 def test_engine_fed_reference_encoder_emulated(tmp_path, emu_lib, kind, n, hb):
     from oracle import refbind as rb
     from nlzm_b200 import synth
     _need(rb.REF_EMU_SO)
     _need(rb.REF_R0)
-    _roundtrip(tmp_path, synth.make(kind, n), hb, emu=True, block_len=150_000)
+    _roundtrip(tmp_path, synth.make(kind, n), hb, emu=True, block_len=60_000)
 
 
 @pytest.mark.gpu

@@ -21,7 +21,7 @@ def _worker(rank, world, port, q):
     from nlzm_b200 import _lib, synth, sharding
     from nlzm_b200.matchfinder import MatchFinders
     emu = _lib.bind_prototypes(C.CDLL(os.path.join(ROOT, "tests", "emu", "libnlzm_mf_emu.so")))
-    x = synth.longrange(260_000, 91)                     # replicated input
+    x = synth.longrange(110_000, 91)                     # replicated input
     b, e = sharding.shard_range(x.size, rank, world)
     with MatchFinders(emu) as mf:
         mf.Init(15, x)
@@ -48,7 +48,7 @@ def test_two_rank_sharding(emu_lib, orc):
         p.join(60)
         assert p.exitcode == 0
     assert tmax == 2.0
-    x = synth.longrange(260_000, 91)
+    x = synth.longrange(110_000, 91)
     off, dist_, ln = sharding.concat_views([(b, e, o, s) for (b, e, o, s) in parts])
     ref = orc.find(x, 15, orc.F_ALL)
     assert orc.csr_equal(ref, (off, dist_, ln))
