@@ -91,6 +91,8 @@ struct DcParams {
     const Elem *cur;     // level k-1 arrays
     Elem *nxt;           // level k arrays
     u32 *corank;         // per cur index of a left-half element: its co-rank in the right half
+    u32 origin;          // merge levels: cur/nxt/corank/part are shifted by this many elements (cross pass)
+    u32 cross;           // 1 = query-only pass between neighbouring window-sized blocks: nothing is stored
     const u32 *part;     // merge-path split per output tile (merge levels)
     PtrEntry *ptr;       // indexed by universe-relative position
     TupleSink sink;
@@ -461,7 +463,7 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
     const u32 o1 = (o0 + NLZM_MT_TILE) < seg_end ? (o0 + NLZM_MT_TILE) : seg_end;
     const u32 cnt = o1 - o0;
     if (s.r_len == 0) {                                         // lonely left half at the end of the universe
-        for (u32 i = tid; i < cnt; i += NLZM_MT_THREADS) p.nxt[o0 + i] = p.cur[o0 + i];
+        if (!p.cross) for (u32 i = tid; i < cnt; i += NLZM_MT_THREADS) p.nxt[o0 + i] = p.cur[o0 + i];
         return;
     }
     const u32 d0 = o0 - s.base, d1 = o1 - s.base;
@@ -517,7 +519,7 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         const u64 a_abs = p.u0 + pos;
         u32 cap;
         const u32 best_in = elem_best(e.tail);
-        if (!dc_query_cap(p, a_abs, cap) || best_in >= cap || pos - (s.r_beg - 1) > p.g.W - 1) continue;
+        if (!dc_query_cap(p, a_abs, cap) || best_in >= cap || pos - (p.origin + s.r_beg - 1) > p.g.W - 1) continue;
         const u32 li = lcnt[o];
         NLZM_STAT(0, 1);
         bool want = false;
@@ -547,7 +549,7 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
     NLZM_CTA_SYNC();
 
     // ---- coalesced stores: merged elements, and the co-rank of every left element
-    {
+    if (!p.cross) {
         const V16 *S = (const V16 *)el;
         V16 *G = (V16 *)(p.nxt + o0);
         for (u32 c = tid; c < cnt * 2; c += NLZM_MT_THREADS) G[c] = S[(u32)src[c >> 1] * 2 + (c & 1)];

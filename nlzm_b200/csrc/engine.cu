@@ -263,8 +263,12 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
     dp.sink = sink();
     CKI(launch_dc_base(dp, (n + NLZM_BASE_TILE - 1) / NLZM_BASE_TILE, NLZM_BASE_SMEM, st));
     dp.corank = rank.as<u32>();          // ranks now live inside the element keys
+    dp.origin = 0;
+    dp.cross = 0;
     int cur = 0;
-    for (u64 h = NLZM_BASE_TILE; h < n; h <<= 1) {
+    // binary levels only up to window-sized segments: nothing further back than W-1 can be a candidate
+    const u64 h_end = n < (u64)g.W ? n : (u64)g.W;
+    for (u64 h = NLZM_BASE_TILE; h < h_end; h <<= 1) {
         dp.cur = el[cur].as<Elem>();
         dp.nxt = el[cur ^ 1].as<Elem>();
         dp.h = (u32)h;
@@ -272,6 +276,25 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
         CKI(launch_dc_merge_tile(dp, tiles, NLZM_MT_SMEM, st));
         launch_dc_link(dp, n, st);
         cur ^= 1;
+    }
+    // ... then every window-sized block queries the block before it (two passes: even and odd pairs);
+    // these passes store nothing: no level above them exists
+    if (n > (u64)g.W && (u64)g.W >= NLZM_BASE_TILE) {
+        for (u32 parity = 0; parity < 2; parity++) {
+            const u64 origin = (u64)parity * g.W;
+            if (n <= origin + g.W) break;
+            DcParams cp = dp;
+            cp.origin = (u32)origin;
+            cp.cross = 1;
+            cp.n = (u32)(n - origin);
+            cp.h = g.W;
+            cp.cur = el[cur].as<Elem>() + origin;
+            cp.nxt = nullptr;
+            cp.corank = nullptr;
+            const u64 ctiles = (cp.n + NLZM_MT_TILE - 1) / NLZM_MT_TILE;
+            launch_dc_partition(cp, ctiles, st);
+            CKI(launch_dc_merge_tile(cp, ctiles, NLZM_MT_SMEM, st));
+        }
     }
 
     // --- lengths 2..3 inside a bucket (only windows < 2^19)
