@@ -118,7 +118,9 @@ DEV bool dc_query_cap(const DcParams &p, u64 a_abs, u32 &cap) {
 #define NLZM_BASE_LOG 12
 #endif
 #define NLZM_BASE_TILE (1u << NLZM_BASE_LOG)
+#ifndef NLZM_BASE_IPT
 #define NLZM_BASE_IPT 8u
+#endif
 #define NLZM_BASE_THREADS (NLZM_BASE_TILE / NLZM_BASE_IPT)
 #define NLZM_BASE_TEXT (NLZM_BASE_TILE + NLZM_MATCH_MAX + 8)
 #define NLZM_BASE_SMEM (NLZM_BASE_TILE * 20 + NLZM_BASE_TEXT + 8)
@@ -360,8 +362,12 @@ NLZM_KERNEL_CTA(dc_base, DcParams, NLZM_BASE_THREADS)
 // ================================================================================================
 // merge levels
 // ================================================================================================
+#ifndef NLZM_MT_THREADS
 #define NLZM_MT_THREADS 256
+#endif
+#ifndef NLZM_MT_ITEMS
 #define NLZM_MT_ITEMS 4
+#endif
 #define NLZM_MT_TILE (NLZM_MT_THREADS * NLZM_MT_ITEMS)
 #define NLZM_MT_SMEM ((NLZM_MT_TILE + 2) * 32 + NLZM_MT_TILE * 8 + 16)
 

@@ -1,7 +1,8 @@
 # scratch: first timing of the engine on the GPU box
 import sys, time, numpy as np
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from nlzm_b200 import synth
+from nlzm_b200 import synth, _lib
+if os.environ.get('NLZM_MF_LIB'): _lib.LIB_PATH = os.environ['NLZM_MF_LIB']   # tuning variants (tools only)
 from nlzm_b200.matchfinder import MatchFinders, profile, kernel_times
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 hb = int(sys.argv[2]) if len(sys.argv) > 2 else 24
