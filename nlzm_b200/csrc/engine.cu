@@ -111,7 +111,8 @@ struct nlzm_mf {
 
     DevBuf k64[2], v32[2], rank, ptr, aux0, aux1, el[2], part;     // stages S/T
     DevBuf tk[2], tv[2], tcount, keep, out_idx;                    // tuples / merge
-    DevBuf e_k[2], e_v[2], e_inv;                                  // HT / BT-short event sorts
+    DevBuf e_k[2], e_v[2], e_inv;                                  // BT short-length bucket sort (small windows)
+    DevBuf ht_tab, ht_ps, ht_pl, ht_pr;                            // HT: per-tile last-access tables, PS/PL/PR
     DevBuf hblk, sl_k[2], sl_v[2], sl_cnt, sl_off;                 // RK table
     DevBuf hit_k[2], hit_v[2], hit_len, hit_count, iv, n_iv, val_k, val_v;       // RK hits / carry intervals
     DevBuf scalars;                                                // misc device scalars
@@ -330,22 +331,19 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
 // ------------------------------------------------------------------------------------------------
 int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     if (g.flen < 4) return 0;
-    const u64 pe = own_e < g.flen - 3 ? own_e : g.flen - 3;          // accesses happen while 4 bytes are visible
-    if (pe <= own_b) return 0;
-    const u64 m = pe * c.rows;                                       // events of the whole prefix (tables never age)
-    CKI(ensure(e_k[0], m * 4)); CKI(ensure(e_k[1], m * 4));
-    CKI(ensure(e_v[0], m * 4)); CKI(ensure(e_v[1], m * 4));
-    const u64 first_ev = own_b * c.rows;
-    CKI(ensure(e_inv, (m - first_ev) * 4));
-    CKI(ensure_prim(m));
-    HtEventParams ep{x.as<u8>(), c, e_k[0].as<u32>(), e_v[0].as<u32>()};
-    launch_ht_event(ep, pe, st);
-    int sel = 0;
-    CKI(prim_sort_pairs32(tmp, e_k[0].as<u32>(), e_k[1].as<u32>(), e_v[0].as<u32>(), e_v[1].as<u32>(), m, 0, (int)c.bits + 1, st, &sel));
-    HtInvParams vp{e_v[sel].as<u32>(), e_inv.as<u32>(), (u32)first_ev};
-    launch_ht_inv(vp, m, st);
-    HtFindParams fp{x.as<u8>(), g, c, e_k[sel].as<u32>(), e_v[sel].as<u32>(), e_inv.as<u32>(), (u32)first_ev, (u32)m, own_b, sink()};
-    launch_ht_find(fp, pe - own_b, st);
+    const u64 n_acc = own_e < g.flen - 3 ? own_e : g.flen - 3;       // accesses happen while 4 bytes are visible
+    if (n_acc <= own_b) return 0;
+    const u64 nc = 1ull << c.bits;
+    const u64 n_tiles = (n_acc + NLZM_HT_TILE - 1) / NLZM_HT_TILE;   // tables never age: tiles cover the whole prefix
+    CKI(ensure(ht_tab, n_tiles * nc * 4));
+    CKI(ensure(ht_ps, n_acc * 4));
+    if (c.rows == 2) { CKI(ensure(ht_pl, n_acc * 4)); CKI(ensure(ht_pr, n_acc * 4)); }
+    HtTableParams tp{x.as<u8>(), c, n_acc, (u32)n_tiles, ht_tab.as<u32>(), ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>()};
+    CKI(launch_ht_tile_last(tp, n_tiles, nc * 4, st));
+    launch_ht_tile_scan(tp, nc, st);
+    CKI(launch_ht_prev(tp, n_tiles, nc * 4, st));
+    HtFindParams fp{x.as<u8>(), g, c, ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>(), own_b, sink()};
+    launch_ht_find(fp, n_acc - own_b, st);
     return 0;
 }
 
@@ -408,7 +406,11 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     CK(cudaMemsetAsync(n_valid, 0, 4, st));
     RkExtendParams xp{x.as<u8>(), g, hit_k[0].as<u64>(), hit_v[0].as<u32>(), hit_len.as<u32>(),
                       hit_k[1].as<u64>(), hit_v[1].as<u32>(), n_valid};
+#ifndef NLZM_EMU
+    launch_rk_extend_warp(xp, n_hits, st);
+#else
     launch_rk_extend(xp, n_hits, st);
+#endif
     u32 nv = 0;
     CK(cudaMemcpyAsync(&nv, n_valid, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -610,7 +612,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
     }
     DevBuf *all[] = {&mf->x, &mf->k64[0], &mf->k64[1], &mf->v32[0], &mf->v32[1], &mf->rank, &mf->ptr, &mf->el[0], &mf->el[1], &mf->part, &mf->aux0,
                      &mf->aux1, &mf->tk[0], &mf->tk[1], &mf->tv[0], &mf->tv[1], &mf->tcount, &mf->keep, &mf->out_idx,
-                     &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
+                     &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->ht_tab, &mf->ht_ps, &mf->ht_pl, &mf->ht_pr, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
                      &mf->sl_v[0], &mf->sl_v[1], &mf->sl_cnt, &mf->sl_off, &mf->hit_k[0], &mf->hit_k[1], &mf->hit_v[0],
                      &mf->hit_v[1], &mf->hit_len, &mf->hit_count, &mf->iv, &mf->n_iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf};
     for (DevBuf *b : all) mf->release(*b);

@@ -1,13 +1,20 @@
-// Stage H — HT2 / HT3 short-match finders (NLZM.cpp:893-957) without a table.
+// Stage H — HT2 / HT3 short-match finders (NLZM.cpp:893-957) without the tables.
 //
 // The reference keeps `rows << bits` u32 cells; an access with bucket b reads cells b .. b+rows-1
 // (rows overlap because the row pointer is `rows + bucket`, NLZM.cpp:912), then writes its own
-// entry into cell b and pushes the old content of cell b into cell b+1. The content a reader sees
-// is therefore "the last write before me": every access is turned into `rows` write events
-// (cell, time), the events are radix-sorted by cell (stable => time order inside a cell), and a
-// reader takes the event just before its own in the cell's list. A row-1 event carries the old
-// content of the cell to its left at that time, which is resolved the same way (a short chain).
-// MatchFinderHT::Shift as written only clears cell 0 at each ring shift (NLZM.cpp:940-957).
+// entry into cell b and pushes the old content of cell b into cell b+1. What a reader sees in a
+// cell is "the last write before me", and a cell c is written by accesses of bucket c (own entry)
+// and of bucket c-1 (the pushed old content of cell c-1). So everything follows from three numbers
+// per position p with bucket b:  PS[p], PL[p], PR[p] = the last access before p in bucket b, b-1,
+// b+1. They are computed with per-tile "last access" tables:
+//   k_ht_tile_last   per tile of 64 Ki positions: last access per bucket (shared-memory atomicMax)
+//   k_ht_tile_scan   exclusive running max over the tiles, per bucket  => table at every tile start
+//   k_ht_prev        per tile, in position order: one warp walks the tile 32 positions at a time with
+//                    the table in shared memory; accesses inside the same 32 are resolved with shuffles
+//   k_ht_find        per position: resolve the raw cell contents (a short chain when the last writer
+//                    pushed an older entry), then the reference's match / check-bit / window logic
+// MatchFinderHT::Shift as written only clears cell 0 at each ring shift (NLZM.cpp:940-957); tables
+// never age, so PS/PL/PR are built over the whole prefix [0, end) — streaming work, no sort.
 #pragma once
 #include "common.cuh"
 #include "dc_levels.cuh"
@@ -18,75 +25,179 @@ struct HtCfg {
     u32 nbytes;    // 2 or 3 hashed bytes
 };
 
+#define NLZM_HT_TILE 65536u
+#define NLZM_HT_THREADS 256
+
 HD u32 ht_hash(const u8 *__restrict__ x, u64 a, u32 nbytes) {
     u32 v = load4(x, a) & (nbytes == 2 ? 0xFFFFu : 0xFFFFFFu);      // VALUE2 / VALUE3, NLZM.cpp:741-742
     return v * NLZM_HASH_MUL;
 }
 
-struct HtEventParams { const u8 *x; HtCfg c; u32 *keys; u32 *vals; };
-DEV void ht_event_body(const HtEventParams &p, u64 a) {
-    u32 b = ht_hash(p.x, a, p.c.nbytes) >> (32 - p.c.bits);
-    for (u32 r = 0; r < p.c.rows; r++) {
-        p.keys[a * p.c.rows + r] = b + r;            // cell written by this access at row r
-        p.vals[a * p.c.rows + r] = (u32)(a * p.c.rows + r);
+struct HtTableParams {
+    const u8 *x;
+    HtCfg c;
+    u64 n_acc;        // accesses happen at positions [0, n_acc) (4 bytes visible, NLZM.cpp:1515)
+    u32 n_tiles;
+    u32 *tile_last;   // [n_tiles][1 << bits]: last access (+1) per bucket inside the tile, then: before the tile
+    u32 *ps, *pl, *pr;// per position: last access (+1, 0 = none) before it in bucket b, b-1, b+1
+};
+
+// ---- per tile: last access per bucket
+DEV void ht_tile_last_cta(const HtTableParams &p, u32 bid, u32 tid, u8 *smem) {
+    u32 *tab = (u32 *)smem;
+    const u32 nc = 1u << p.c.bits;
+    for (u32 i = tid; i < nc; i += NLZM_HT_THREADS) tab[i] = 0;
+    NLZM_CTA_SYNC();
+    const u64 t0 = (u64)bid * NLZM_HT_TILE;
+    const u64 t1 = t0 + NLZM_HT_TILE < p.n_acc ? t0 + NLZM_HT_TILE : p.n_acc;
+    for (u64 a = t0 + tid; a < t1; a += NLZM_HT_THREADS)
+        nlzm_atomic_max(tab + (ht_hash(p.x, a, p.c.nbytes) >> (32 - p.c.bits)), (u32)a + 1u);
+    NLZM_CTA_SYNC();
+    u32 *out = p.tile_last + (u64)bid * nc;
+    for (u32 i = tid; i < nc; i += NLZM_HT_THREADS) out[i] = tab[i];
+}
+NLZM_KERNEL_CTA(ht_tile_last, HtTableParams, NLZM_HT_THREADS)
+
+// ---- exclusive running max over tiles (one thread per bucket, coalesced across buckets)
+DEV void ht_tile_scan_body(const HtTableParams &p, u64 b) {
+    const u32 nc = 1u << p.c.bits;
+    u32 run = 0;
+    for (u32 t = 0; t < p.n_tiles; t++) {
+        u32 *cell = p.tile_last + (u64)t * nc + b;
+        const u32 v = *cell;
+        *cell = run;
+        run = v > run ? v : run;
     }
 }
-NLZM_KERNEL_1D(ht_event, HtEventParams)
+NLZM_KERNEL_1D(ht_tile_scan, HtTableParams)
 
-// inverse permutation, only for events at or after `first_ev` (the range being answered): tables
-// never age, so the sorted event list covers the whole prefix, but only own events start a lookup
-struct HtInvParams { const u32 *vals; u32 *inv; u32 first_ev; };
-DEV void ht_inv_body(const HtInvParams &p, u64 j) {
-    const u32 v = p.vals[j];
-    if (v >= p.first_ev) p.inv[v - p.first_ev] = (u32)j;
+// ---- per tile, in position order: PS / PL / PR
+#if !defined(NLZM_EMU)
+__global__ void __launch_bounds__(32) k_ht_prev(const HtTableParams p) {
+    extern __shared__ __align__(16) u8 nlzm_smem[];
+    u32 *tab = (u32 *)nlzm_smem;
+    const u32 nc = 1u << p.c.bits, lane = threadIdx.x;
+    const u32 *init = p.tile_last + (u64)blockIdx.x * nc;
+    for (u32 i = lane; i < nc; i += 32) tab[i] = init[i];
+    __syncwarp();
+    const u64 t0 = (u64)blockIdx.x * NLZM_HT_TILE;
+    const u64 t1 = t0 + NLZM_HT_TILE < p.n_acc ? t0 + NLZM_HT_TILE : p.n_acc;
+    const u32 shift = 32 - p.c.bits;
+    for (u64 base = t0; base < t1; base += 32) {
+        const u64 a = base + lane;
+        const bool live = a < t1;
+        const u32 b = live ? ht_hash(p.x, a, p.c.nbytes) >> shift : 0xFFFFFFF0u;     // never equals a bucket or its neighbours
+        u32 vs = 0, vl = 0, vr = 0;
+        if (live) {
+            vs = tab[b];
+            if (p.c.rows == 2) {
+                if (b > 0) vl = tab[b - 1];
+                if (b + 1 < nc) vr = tab[b + 1];
+            }
+        }
+        // Every lane publishes its access; if nobody else's shows up in the three cells a lane looks at,
+        // the 32 accesses do not interact (the common case) and the values read above are final.
+        __syncwarp();                                                    // all lanes have read the pre-step table
+        if (live) tab[b] = (u32)a + 1u;
+        __syncwarp();
+        bool clash = false;
+        if (live) {
+            const u32 lo = (u32)base, me = (u32)a + 1u;
+            const u32 cs = tab[b];
+            clash = cs != me;                                            // another lane has my bucket
+            if (p.c.rows == 2) {
+                if (b > 0) { const u32 v = tab[b - 1]; clash |= v > lo; }       // a lane of this step accessed bucket b-1
+                if (b + 1 < nc) { const u32 v = tab[b + 1]; clash |= v > lo; }
+            }
+        }
+        if (__any_sync(0xFFFFFFFFu, clash)) {
+            // accesses inside these 32 positions, in order: a later lane overrides an earlier one
+            for (u32 j = 0; j < 31; j++) {
+                const u32 bj = __shfl_sync(0xFFFFFFFFu, b, j);
+                if (j < lane) {
+                    const u32 pj = (u32)(base + j) + 1u;
+                    if (bj == b) vs = pj;
+                    if (bj + 1 == b) vl = pj;
+                    if (bj == b + 1) vr = pj;
+                }
+            }
+            // the table must hold the LAST access of each bucket: the highest lane of each bucket writes
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, b);
+            __syncwarp();
+            if (live && (peers >> lane) == 1u) tab[b] = (u32)a + 1u;
+        }
+        if (live) {
+            p.ps[a] = vs;
+            if (p.c.rows == 2) { p.pl[a] = vl; p.pr[a] = vr; }
+        }
+        __syncwarp();
+    }
 }
-NLZM_KERNEL_1D(ht_inv, HtInvParams)
+static inline int launch_ht_prev(const HtTableParams &p, u64 grid, size_t smem, cudaStream_t st) {
+    if (grid == 0) return 0;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_ht_prev, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    nlzm_launch_begin("k_ht_prev", st);
+    k_ht_prev<<<(unsigned)grid, 32, smem, st>>>(p);
+    nlzm_launch_end(st);
+    return (int)cudaGetLastError();
+}
+#else
+// emulation: the same definition, one position after the other
+static inline int launch_ht_prev(const HtTableParams &p, u64 grid, size_t, cudaStream_t st) {
+    nlzm_launch_begin("k_ht_prev", st);
+    const u32 nc = 1u << p.c.bits, shift = 32 - p.c.bits;
+    std::vector<u32> tab(nc);
+    for (u64 t = 0; t < grid; t++) {
+        for (u32 i = 0; i < nc; i++) tab[i] = p.tile_last[t * nc + i];
+        const u64 t0 = t * NLZM_HT_TILE, t1 = t0 + NLZM_HT_TILE < p.n_acc ? t0 + NLZM_HT_TILE : p.n_acc;
+        for (u64 a = t0; a < t1; a++) {
+            const u32 b = ht_hash(p.x, a, p.c.nbytes) >> shift;
+            p.ps[a] = tab[b];
+            if (p.c.rows == 2) { p.pl[a] = b > 0 ? tab[b - 1] : 0; p.pr[a] = b + 1 < nc ? tab[b + 1] : 0; }
+            tab[b] = (u32)a + 1u;
+        }
+    }
+    nlzm_launch_end(st);
+    return 0;
+}
+#endif
 
 struct HtFindParams {
     const u8 *x;
     Geom g;
     HtCfg c;
-    const u32 *skeys;    // sorted cells
-    const u32 *svals;    // event ids in (cell, time) order
-    const u32 *inv;      // event id - first_ev -> index in the sorted arrays
-    u32 first_ev;        // first event id covered by inv
-    u32 n_ev;            // number of sorted events
+    const u32 *ps, *pl, *pr;
     u64 own_b;
     TupleSink sink;
 };
 
-// index of event `ev` (which writes `cell`) in the sorted arrays
-DEV u32 ht_event_index(const HtFindParams &p, u32 ev, u32 cell) {
-    if (ev >= p.first_ev) return p.inv[ev - p.first_ev];
-    // an event before the answered range (rare: a chain that reaches back): binary search by (cell, id)
-    u32 lo = 0, hi = p.n_ev;
-    while (lo < hi) {
-        const u32 mid = lo + ((hi - lo) >> 1);
-        const u32 c = p.skeys[mid];
-        if (c < cell || (c == cell && p.svals[mid] < ev)) lo = mid + 1; else hi = mid;
-    }
-    return lo;
+// entry an access at position w stores: full shifted position OR-ed with the check bits (NLZM.cpp:913)
+DEV u32 ht_entry(const HtFindParams &p, u64 w) {
+    const u32 cmask = (1u << (32 - p.g.hb)) - 1;
+    return geom_P(p.g, w) | ((ht_hash(p.x, w, p.c.nbytes) & cmask) << p.g.hb);
 }
 
-// raw u32 content of the cell that event `ev` (of the access at time t) is about to overwrite
-DEV u32 ht_cell_before(const HtFindParams &p, u32 ev, u64 t, u32 cell0) {
-    const u32 cmask = (1u << (32 - p.g.hb)) - 1;
-    u32 j = ht_event_index(p, ev, cell0);
+// raw u32 content of cell `cell` as seen by a reader at time t, given the last accesses (+1) before t
+// of bucket `cell` (w0: writes its own entry) and of bucket `cell - 1` (w1: pushes cell-1's old content)
+DEV u32 ht_cell_value(const HtFindParams &p, u32 cell, u64 t, u32 w0, u32 w1) {
     while (true) {
-        if (j == 0) return NLZM_NONE32;
-        const u32 cell = p.skeys[j];
-        if (p.skeys[j - 1] != cell) return NLZM_NONE32;          // nobody wrote this cell before
-        const u32 pe = p.svals[j - 1];
-        const u64 w = pe / p.c.rows;                            // the writer's position
-        const u32 kind = pe - (u32)w * p.c.rows;
-        if (cell == 0 && geom_epoch(p.g, w) != geom_epoch(p.g, t)) return NLZM_NONE32;   // cleared by a ring shift
-        if (kind == 0) {
-            // the writer stored its own entry: full shifted position OR-ed with the check bits
-            return geom_P(p.g, w) | ((ht_hash(p.x, w, p.c.nbytes) & cmask) << p.g.hb);   // NLZM.cpp:913
+        if (w0 == 0 && w1 == 0) return NLZM_NONE32;                         // never written
+        if (cell == 0) {                                                     // only bucket 0 writes cell 0 ...
+            const u64 w = w0 - 1;
+            if (geom_epoch(p.g, w) != geom_epoch(p.g, t)) return NLZM_NONE32;  // ... and every ring shift clears it
+            return ht_entry(p, w);
         }
-        // the writer pushed the old content of its own bucket cell (cell - 1) here
-        t = w;
-        j = ht_event_index(p, (u32)w * p.c.rows, cell - 1);
+        if (w0 > w1) return ht_entry(p, w0 - 1);
+        const u64 q = w1 - 1;                 // bucket cell-1 accessed at q and pushed the old content of cell-1
+        t = q;
+        cell -= 1;
+        w0 = p.ps[q];
+        w1 = (p.c.rows == 2 && cell > 0) ? p.pl[q] : 0u;
     }
 }
 
@@ -95,13 +206,16 @@ DEV void ht_find_body(const HtFindParams &p, u64 i) {
     const u32 hash = ht_hash(p.x, a, p.c.nbytes);
     const u32 cmask = (1u << (32 - p.g.hb)) - 1;
     const u32 chk = hash & cmask;
+    const u32 b = hash >> (32 - p.c.bits);
     const u32 P = geom_P(p.g, a);
     const u32 rem = geom_rem(p.g, a);
     const u32 cap = rem < NLZM_MATCH_MAX ? rem : NLZM_MATCH_MAX;      // NLZM.cpp:915
     const u64 base = a - P;
+    const u32 ps = p.ps[a];
     u32 best = 1;                                                     // MATCH_MIN - 1, NLZM.cpp:917
     for (u32 r = 0; r < p.c.rows; r++) {
-        const u32 row = ht_cell_before(p, (u32)a * p.c.rows + r, a, (hash >> (32 - p.c.bits)) + r);
+        const u32 row = r == 0 ? ht_cell_value(p, b, a, ps, (p.c.rows == 2 && b > 0) ? p.pl[a] : 0u)
+                               : ht_cell_value(p, b + 1, a, p.pr[a], ps);
         if (best < cap && (row >> p.g.hb) == chk) {
             const u32 sp = row & (p.g.W - 1);
             if (sp < P && P - sp <= p.g.W - 1) {
@@ -115,3 +229,11 @@ DEV void ht_find_body(const HtFindParams &p, u64 i) {
     }
 }
 NLZM_KERNEL_1D(ht_find, HtFindParams)
+
+// bucket sort helper kept for bt_short.cuh (small windows): inverse permutation of a sorted value list
+struct HtInvParams { const u32 *vals; u32 *inv; u32 first_ev; };
+DEV void ht_inv_body(const HtInvParams &p, u64 j) {
+    const u32 v = p.vals[j];
+    if (v >= p.first_ev) p.inv[v - p.first_ev] = (u32)j;
+}
+NLZM_KERNEL_1D(ht_inv, HtInvParams)

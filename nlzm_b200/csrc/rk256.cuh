@@ -104,6 +104,50 @@ DEV void rk_extend_body(const RkExtendParams &p, u64 i) {
 }
 NLZM_KERNEL_1D(rk_extend, RkExtendParams)
 
+#ifndef NLZM_EMU
+// Warp-cooperative version used on the GPU: one warp per raw hit. Each lane compares 8 bytes of a
+// 256-byte stripe per step (coalesced on both streams), the first mismatching lane is found with
+// __ballot_sync / __ffs, and the byte inside it with a trailing-zero count. Matches run up to 65535
+// bytes (NLZM.cpp:1096-1097), so a single thread per hit serialises badly on redundant data.
+__global__ void __launch_bounds__(256) k_rk_extend_warp(const RkExtendParams p, u32 n_hits) {
+    const u32 warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    if (warp >= n_hits) return;
+    const u64 a = p.hit_pos[warp];
+    const u32 d = p.hit_dist[warp];
+    const u32 cap = geom_rem(p.g, a) & 0xFFFFu;
+    u32 m = 0;
+    while (m < cap) {
+        const u32 off = m + lane * 8;
+        u64 diff = 0;
+        if (off < cap) diff = load8(p.x, a - d + off) ^ load8(p.x, a + off);      // bytes past cap are ignored below
+        const unsigned bad = __ballot_sync(0xFFFFFFFFu, diff != 0);
+        if (bad) {
+            const int first = __ffs(bad) - 1;
+            const u64 dd = __shfl_sync(0xFFFFFFFFu, diff, first);
+            m += (u32)first * 8 + ((u32)(__ffsll((long long)dd) - 1) >> 3);
+            break;
+        }
+        m += 256;
+    }
+    if (m > cap) m = cap;
+    if (lane == 0) {
+        p.hit_len[warp] = m;
+        if (m >= match_min(d)) {
+            u32 j = atomicAdd(p.valid_count, 1u);
+            p.valid_pos[j] = a;
+            p.valid_idx[j] = warp;
+        }
+    }
+}
+static inline void launch_rk_extend_warp(const RkExtendParams &p, u64 n_hits, cudaStream_t st) {
+    if (n_hits == 0) return;
+    nlzm_launch_begin("k_rk_extend_warp", st);
+    k_rk_extend_warp<<<(unsigned)((n_hits * 32 + 255) / 256), 256, 0, st>>>(p, (u32)n_hits);
+    nlzm_launch_end(st);
+}
+#endif
+
 struct RkInterval { u64 start; u32 dist; u32 len; u64 end; };
 
 struct RkChainParams {
