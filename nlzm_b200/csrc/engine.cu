@@ -338,10 +338,10 @@ int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     CKI(ensure(ht_tab, n_tiles * nc * 4));
     CKI(ensure(ht_ps, n_acc * 4));
     if (c.rows == 2) { CKI(ensure(ht_pl, n_acc * 4)); CKI(ensure(ht_pr, n_acc * 4)); }
-    HtTableParams tp{x.as<u8>(), c, n_acc, (u32)n_tiles, ht_tab.as<u32>(), ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>()};
+    HtTableParams tp{x.as<u8>(), c, n_acc, g.flen + NLZM_X_PAD, (u32)n_tiles, ht_tab.as<u32>(), ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>()};
     CKI(launch_ht_tile_last(tp, n_tiles, nc * 4, st));
     launch_ht_tile_scan(tp, nc, st);
-    CKI(launch_ht_prev(tp, n_tiles, nc * 4, st));
+    CKI(launch_ht_prev(tp, n_tiles, nc * 4 + NLZM_HT_STAGE + 16, st));
     HtFindParams fp{x.as<u8>(), g, c, ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>(), own_b, sink()};
     launch_ht_find(fp, n_acc - own_b, st);
     return 0;

@@ -27,6 +27,7 @@ struct HtCfg {
 
 #define NLZM_HT_TILE 65536u
 #define NLZM_HT_THREADS 256
+#define NLZM_HT_STAGE 2048u                     // text bytes staged in shared memory by k_ht_prev
 
 HD u32 ht_hash(const u8 *__restrict__ x, u64 a, u32 nbytes) {
     u32 v = load4(x, a) & (nbytes == 2 ? 0xFFFFu : 0xFFFFFFu);      // VALUE2 / VALUE3, NLZM.cpp:741-742
@@ -37,6 +38,7 @@ struct HtTableParams {
     const u8 *x;
     HtCfg c;
     u64 n_acc;        // accesses happen at positions [0, n_acc) (4 bytes visible, NLZM.cpp:1515)
+    u64 x_limit;      // 8-byte words may be read at offsets <= x_limit (input length + padding - 8)
     u32 n_tiles;
     u32 *tile_last;   // [n_tiles][1 << bits]: last access (+1) per bucket inside the tile, then: before the tile
     u32 *ps, *pl, *pr;// per position: last access (+1, 0 = none) before it in bucket b, b-1, b+1
@@ -83,10 +85,28 @@ __global__ void __launch_bounds__(32) k_ht_prev(const HtTableParams p) {
     const u64 t0 = (u64)blockIdx.x * NLZM_HT_TILE;
     const u64 t1 = t0 + NLZM_HT_TILE < p.n_acc ? t0 + NLZM_HT_TILE : p.n_acc;
     const u32 shift = 32 - p.c.bits;
+    const u32 vmask = p.c.nbytes == 2 ? 0xFFFFu : 0xFFFFFFu;
+    u32 *stage = tab + nc;                         // NLZM_HT_STAGE + 8 text bytes of the walk, refilled every 64 steps
     for (u64 base = t0; base < t1; base += 32) {
+        const u32 in_stage = (u32)(base - t0) & (NLZM_HT_STAGE - 1);
+        if (in_stage == 0) {
+            // coalesced refill: the global-load latency is paid once per 2 KiB instead of once per step
+            __syncwarp();
+            const u64 *src = (const u64 *)(p.x + base);                  // base is a multiple of 32: aligned
+            u64 *dst = (u64 *)stage;
+            for (u32 i = lane; i < NLZM_HT_STAGE / 8 + 1; i += 32) dst[i] = (base + 8ull * i <= p.x_limit) ? src[i] : 0ull;
+            __syncwarp();
+        }
         const u64 a = base + lane;
         const bool live = a < t1;
-        const u32 b = live ? ht_hash(p.x, a, p.c.nbytes) >> shift : 0xFFFFFFF0u;     // never equals a bucket or its neighbours
+        u32 b = 0xFFFFFFF0u;                                             // never equals a bucket or its neighbours
+        if (live) {
+            const u32 o = in_stage + lane;                               // byte offset inside the staged text
+            const u32 w0 = stage[o >> 2], w1 = stage[(o >> 2) + 1];
+            const u32 sh = (o & 3) * 8;
+            const u32 v = sh ? ((w0 >> sh) | (w1 << (32 - sh))) : w0;
+            b = ((v & vmask) * NLZM_HASH_MUL) >> shift;
+        }
         u32 vs = 0, vl = 0, vr = 0;
         if (live) {
             vs = tab[b];
