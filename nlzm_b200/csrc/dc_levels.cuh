@@ -175,23 +175,26 @@ DEV u32 base_merge_path(const BaseSmem &s, const u16 *L, u32 l_len, const u16 *R
 }
 
 // Walk one chain; the caller has already established that the first 4 bytes of `start` match.
-DEV void base_walk(const DcParams &p, const BaseSmem &s, u32 a, u64 a_abs, u32 cap, u32 best_in, u32 start, const u16 *link,
-                   u32 &new_best) {
-    u32 c = start, pend_len = 0, pend_c = 0, lim = cap;
+DEV u32 base_lcp4(const BaseSmem &s, u32 c, u32 a, u32 lim) {     // first 4 bytes are known to be equal
+    u32 l = 4;
+    while (l < lim && s.text[c + l] == s.text[a + l]) ++l;
+    return l < lim ? l : lim;
+}
+
+// (dom_c, dom_l): the other side's first candidate, see dc_walk
+DEV void base_walk(const DcParams &p, const BaseSmem &s, u32 a, u64 a_abs, u32 best_in, u32 start, u32 first_l, const u16 *link,
+                   u32 dom_c, u32 dom_l, u32 &new_best) {
+    u32 c = start, l = first_l, pend_len = 0, pend_c = 0;
     const u32 ka = s.k4[a];
-    while (c != NLZM_L16_NONE) {
-        if (s.k4[c] != ka) break;                          // lcp < 4 can never beat best (>= 3)
-        u32 l = 4;
-        while (l < lim && s.text[c + l] == s.text[a + l]) ++l;
-        if (l > lim) l = lim;
-        if (l <= best_in) break;
-        if (pend_len && l < pend_len) dc_emit(p, a_abs, a - pend_c, pend_len);
+    while (l > best_in) {
+        if (pend_len && l < pend_len && !(dom_l >= pend_len && dom_c > pend_c)) dc_emit(p, a_abs, a - pend_c, pend_len);
         pend_len = l; pend_c = c;       // equal lcp: the nearer element replaces the farther one
-        lim = l;                        // lcp never grows along the chain
         if (l > new_best) new_best = l;
         c = link[c];
+        if (c == NLZM_L16_NONE || s.k4[c] != ka) break;      // lcp < 4 can never beat best (>= 3)
+        l = base_lcp4(s, c, a, l);                           // lcp never grows along the chain
     }
-    if (pend_len) dc_emit(p, a_abs, a - pend_c, pend_len);
+    if (pend_len && !(dom_l >= pend_len && dom_c > pend_c)) dc_emit(p, a_abs, a - pend_c, pend_len);
 }
 
 DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
@@ -288,8 +291,9 @@ DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
             const u32 best_in = s.best[pos];
             if (best_in >= cap) continue;
             u32 nb = best_in;
-            if (hit_l) base_walk(p, s, pos, a_abs, cap, best_in, cl, s.pg, nb);
-            if (hit_r) base_walk(p, s, pos, a_abs, cap, best_in, cr, s.ng, nb);
+            const u32 ll = hit_l ? base_lcp4(s, cl, pos, cap) : 0u, lr = hit_r ? base_lcp4(s, cr, pos, cap) : 0u;
+            if (hit_l) base_walk(p, s, pos, a_abs, best_in, cl, ll, s.pg, cr, lr > best_in ? lr : 0u, nb);
+            if (hit_r) base_walk(p, s, pos, a_abs, best_in, cr, lr, s.ng, cl, ll > best_in ? ll : 0u, nb);
             if (nb != best_in) s.best[pos] = (u16)nb;
         }
         NLZM_CTA_SYNC();
@@ -425,17 +429,20 @@ DEV u32 elem_pair_lcp(const DcParams &p, const Elem &a, const Elem &b, u32 lim) 
 // (prefix, link lcp) sits in shared memory; the lcp with every further chain element follows from the
 // link lcps stored with the pointers: lcp(a, pg(c)) = min(lcp(a, c), lcp(c, pg(c))). One 32-byte ptr[]
 // read per hop, none at all when the chain ends at the neighbour.
-DEV void dc_walk(const DcParams &p, const Elem &ea, u64 a_abs, u32 cap, u32 best_in, const Elem *first, bool left, u32 &new_best) {
+// (dom_c, dom_l): the other side's first candidate; anything it dominates (nearer and at least as long) would
+// only be merged away later, so it is not queued.
+DEV void dc_walk(const DcParams &p, const Elem &ea, u64 a_abs, u32 best_in, const Elem *first, u32 first_l, bool left,
+                 u32 dom_c, u32 dom_l, u32 &new_best) {
     if (!first) return;
     const u32 a_rel = (u32)ea.key;
     u32 c = (u32)first->key;
-    u32 l = elem_pair_lcp(p, ea, *first, cap);
+    u32 l = first_l;
     u32 link = left ? elem_lpg(first->tail) : elem_lng(first->tail);
     bool have_entry = false;
     PtrEntry en;
     u32 pend_len = 0, pend_c = 0;
     while (l > best_in) {
-        if (pend_len && l < pend_len) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
+        if (pend_len && l < pend_len && !(dom_l >= pend_len && dom_c > pend_c)) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
         pend_len = l; pend_c = c;                              // equal lcp: the nearer element replaces the farther one
         if (l > new_best) new_best = l;
         const u32 l_next = l < link ? l : link;                // lcp never grows along the chain
@@ -449,7 +456,7 @@ DEV void dc_walk(const DcParams &p, const Elem &ea, u64 a_abs, u32 cap, u32 best
         have_entry = true;
         link = left ? en.lpg : en.lng;
     }
-    if (pend_len) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
+    if (pend_len && !(dom_l >= pend_len && dom_c > pend_c)) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
 }
 
 // One CTA produces NLZM_MT_TILE consecutive elements of the merged level array:
@@ -548,8 +555,11 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         const u32 best_in = elem_best(ea.tail);
         const u32 li = lcnt[o];
         u32 nb = best_in;
-        dc_walk(p, ea, a_abs, cap, best_in, (l0 + li > 0) ? &el[li] : nullptr, true, nb);
-        dc_walk(p, ea, a_abs, cap, best_in, (l0 + li < s.l_len) ? &el[li + 1] : nullptr, false, nb);
+        const Elem *fl = (l0 + li > 0) ? &el[li] : nullptr, *fr = (l0 + li < s.l_len) ? &el[li + 1] : nullptr;
+        const u32 ll = fl ? elem_pair_lcp(p, ea, *fl, cap) : 0u, lr = fr ? elem_pair_lcp(p, ea, *fr, cap) : 0u;
+        const u32 cl = fl ? (u32)fl->key : 0u, cr = fr ? (u32)fr->key : 0u;
+        dc_walk(p, ea, a_abs, best_in, fl, ll, true, cr, lr > best_in ? lr : 0u, nb);
+        dc_walk(p, ea, a_abs, best_in, fr, lr, false, cl, ll > best_in ? ll : 0u, nb);
         if (nb != best_in) e.tail = elem_set_best(ea.tail, nb);
     }
     NLZM_CTA_SYNC();

@@ -342,7 +342,7 @@ int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     CKI(launch_ht_tile_last(tp, n_tiles, nc * 4, st));
     launch_ht_tile_scan(tp, nc, st);
     CKI(launch_ht_prev(tp, n_tiles, nc * 4 + NLZM_HT_STAGE + 16, st));
-    HtFindParams fp{x.as<u8>(), g, c, ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>(), own_b, sink()};
+    HtFindParams fp{x.as<u8>(), g, c, ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>(), own_b, (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
     launch_ht_find(fp, n_acc - own_b, st);
     return 0;
 }
@@ -424,7 +424,7 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     u32 niv = 0;
     CK(cudaMemcpyAsync(&niv, n_iv, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    RkExpandParams ex{g, iv.as<RkInterval>(), own_b, own_e, sink()};
+    RkExpandParams ex{g, iv.as<RkInterval>(), own_b, own_e, (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
     launch_rk_expand(ex, niv, st);
     return 0;
 }

@@ -193,6 +193,8 @@ struct HtFindParams {
     HtCfg c;
     const u32 *ps, *pl, *pr;
     u64 own_b;
+    u32 bt_on;           // exhaustive BT4 runs too: it reports a candidate at least as near and as long for every
+                         // match of 4+ bytes, so those need not be queued twice (they would be merged away)
     TupleSink sink;
 };
 
@@ -241,7 +243,7 @@ DEV void ht_find_body(const HtFindParams &p, u64 i) {
             if (sp < P && P - sp <= p.g.W - 1) {
                 const u32 m = lcp_cap(p.x, base + sp, a, cap);
                 if (m > best && m >= match_min(P - sp)) {
-                    tuple_append(p.sink, (u32)i, P - sp, m);
+                    if (m < 4 || !p.bt_on) tuple_append(p.sink, (u32)i, P - sp, m);
                     best = m;
                 }
             }

@@ -208,12 +208,18 @@ DEV void rk_chain_body(const RkChainParams &p, u64) {
 }
 NLZM_KERNEL_1D(rk_chain, RkChainParams)
 
-struct RkExpandParams { Geom g; const RkInterval *iv; u64 own_b, own_e; TupleSink sink; };
+struct RkExpandParams { Geom g; const RkInterval *iv; u64 own_b, own_e; u32 bt_on; TupleSink sink; };
 DEV void rk_expand_body(const RkExpandParams &p, u64 i) {
     const RkInterval v = p.iv[i];
     const u32 mm = match_min(v.dist);
     u64 a = v.start > p.own_b ? v.start : p.own_b;
     u64 end = v.end < p.own_e ? v.end : p.own_e;
+    if (p.bt_on) {
+        // exhaustive BT4 reports a candidate at least as near and as long for every match of 4+ bytes
+        // (see HtFindParams): only the last positions of the carry, where 2..3 bytes remain, can add something
+        const u64 tail = v.start + (v.len > 3 ? v.len - 3 : 0);
+        if (tail > a) a = tail;
+    }
     for (; a < end; a++) {
         if (p.g.flen - a < NLZM_RK_BLOCK) break;                      // RK is not called there (NLZM.cpp:1525)
         u32 r = v.len - (u32)(a - v.start);
