@@ -73,6 +73,9 @@ void nlzm_launch_end(cudaStream_t st) {
 
 static std::string g_create_error;
 
+// device scalars live in one small buffer (u32 slots)
+enum { SC_SUM = 0 /* u64 */, SC_RK_HITS = 8, SC_RK_INTERVALS = 9, SC_RK_VALID = 10 };
+
 #define CK(expr)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (expr);                                                                   \
@@ -114,7 +117,7 @@ struct nlzm_mf {
     DevBuf e_k[2], e_v[2], e_inv;                                  // BT short-length bucket sort (small windows)
     DevBuf ht_tab, ht_ps, ht_pl, ht_pr;                            // HT: per-tile last-access tables, PS/PL/PR
     DevBuf hblk, sl_k[2], sl_v[2], sl_cnt, sl_off;                 // RK table
-    DevBuf hit_k[2], hit_v[2], hit_len, hit_count, iv, n_iv, val_k, val_v;       // RK hits / carry intervals
+    DevBuf hit_k[2], hit_v[2], hit_len, iv, val_k, val_v;          // RK hits / carry intervals
     DevBuf scalars;                                                // misc device scalars
     PrimTemp tmp;
     DevBuf tmpbuf;
@@ -375,8 +378,8 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     CKI(ensure(iv, hit_cap * sizeof(RkInterval)));
     CKI(ensure_prim(n_blk > n_slots + 1 ? n_blk : n_slots + 1));
     CKI(ensure_prim(hit_cap));
-    u32 *hit_count = scalars.as<u32>() + 8;
-    u32 *n_iv = scalars.as<u32>() + 9;
+    u32 *hit_count = scalars.as<u32>() + SC_RK_HITS;
+    u32 *n_iv = scalars.as<u32>() + SC_RK_INTERVALS;
 
     CK(cudaMemsetAsync(sl_cnt.p, 0, (n_slots + 1) * 4, st));
     CK(cudaMemsetAsync(hit_count, 0, 8, st));
@@ -402,7 +405,7 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     if (n_hits == 0) return 0;
     // extension of every raw hit (any order); the few that are real hits are compacted, sorted by
     // position and fed to the sequential carry state machine
-    u32 *n_valid = scalars.as<u32>() + 10;
+    u32 *n_valid = scalars.as<u32>() + SC_RK_VALID;
     CK(cudaMemsetAsync(n_valid, 0, 4, st));
     RkExtendParams xp{x.as<u8>(), g, hit_k[0].as<u64>(), hit_v[0].as<u32>(), hit_len.as<u32>(),
                       hit_k[1].as<u64>(), hit_v[1].as<u32>(), n_valid};
@@ -471,6 +474,7 @@ int nlzm_mf::find_impl(u64 b, u64 e, int si, bool to_host) {
     if (si < 0 || si > 1) return fail(NLZM_MF_E_ARG, "slot must be 0 or 1");
     if (b > e || e > g.flen) return fail(NLZM_MF_E_ARG, "bad range");
     if (e - b > (1ull << 28)) return fail(NLZM_MF_E_ARG, "range larger than 2^28 positions: split it");
+    if (e - b > max_range) return fail(NLZM_MF_E_ARG, "range larger than config.max_range");
 #ifndef NLZM_EMU
     CK(cudaSetDevice(device));
 #endif
@@ -614,7 +618,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
                      &mf->aux1, &mf->tk[0], &mf->tk[1], &mf->tv[0], &mf->tv[1], &mf->tcount, &mf->keep, &mf->out_idx,
                      &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->ht_tab, &mf->ht_ps, &mf->ht_pl, &mf->ht_pr, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
                      &mf->sl_v[0], &mf->sl_v[1], &mf->sl_cnt, &mf->sl_off, &mf->hit_k[0], &mf->hit_k[1], &mf->hit_v[0],
-                     &mf->hit_v[1], &mf->hit_len, &mf->hit_count, &mf->iv, &mf->n_iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf};
+                     &mf->hit_v[1], &mf->hit_len, &mf->iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf};
     for (DevBuf *b : all) mf->release(*b);
 #ifndef NLZM_EMU
     if (mf->st) cudaStreamDestroy(mf->st);

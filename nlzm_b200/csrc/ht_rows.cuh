@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(32) k_ht_prev(const HtTableParams p) {
         // Every lane publishes its access; if nobody else's shows up in the three cells a lane looks at,
         // the 32 accesses do not interact (the common case) and the values read above are final.
         __syncwarp();                                                    // all lanes have read the pre-step table
-        if (live) tab[b] = (u32)a + 1u;
+        if (live) atomicMax(&tab[b], (u32)a + 1u);                       // the last access of a bucket wins
         __syncwarp();
         bool clash = false;
         if (live) {
@@ -141,10 +141,6 @@ __global__ void __launch_bounds__(32) k_ht_prev(const HtTableParams p) {
                     if (bj == b + 1) vr = pj;
                 }
             }
-            // the table must hold the LAST access of each bucket: the highest lane of each bucket writes
-            const unsigned peers = __match_any_sync(0xFFFFFFFFu, b);
-            __syncwarp();
-            if (live && (peers >> lane) == 1u) tab[b] = (u32)a + 1u;
         }
         if (live) {
             p.ps[a] = vs;
