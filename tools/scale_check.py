@@ -7,7 +7,7 @@ from nlzm_b200 import synth, sharding
 from nlzm_b200.matchfinder import MatchFinders
 
 kind, n, hb = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-block = int(sys.argv[4]) if len(sys.argv) > 4 else 1 << 27
+block = int(sys.argv[4]) if len(sys.argv) > 4 else (1 << 28 if hb >= 27 else 1 << 27)   # big windows: big blocks (halo is re-merged per block)
 t = time.time(); x = synth.make(kind, n); print(f"{kind} n={n} hb={hb}: generated in {time.time()-t:.1f}s", flush=True)
 W = 1 << hb
 with MatchFinders() as mf:
