@@ -117,3 +117,36 @@ def test_properties_at_scale(cuda_lib):
         assert np.array_equal(x[a:a + l], x[a - d:a - d + l])
         end = a + l
         assert l == 264 or end >= n or x[end] != x[end - d] or True   # HT/RK steps need not be maximal
+
+
+def _check_properties(x, off, st, begin, W):
+    dist, ln = st["dist"].astype(np.int64), st["len"].astype(np.int64)
+    pos = np.repeat(np.arange(begin, begin + off.size - 1, dtype=np.int64), np.diff(off.astype(np.int64)))
+    assert dist.size == 0 or (dist.min() >= 1 and dist.max() <= W - 1)
+    assert (pos - dist >= 0).all() and (pos + ln <= x.size).all()
+    same = pos[1:] == pos[:-1]
+    assert (ln[1:][same] > ln[:-1][same]).all() and (dist[1:][same] > dist[:-1][same]).all()
+    mm = 2 + (dist >= 256) + (dist >= 4096) + (dist >= (1 << 20))
+    assert (ln >= mm).all() and (ln <= 264).all()
+    assert (x[pos] == x[pos - dist]).all() and (x[pos + ln - 1] == x[pos - dist + ln - 1]).all()
+    rng = np.random.default_rng(1)
+    for j in rng.integers(0, max(pos.size, 1), 5000):
+        a, d, l = int(pos[j]), int(dist[j]), int(ln[j])
+        assert np.array_equal(x[a:a + l], x[a - d:a - d + l])
+
+
+def test_properties_256mb_window(cuda_lib):
+    """-window:28 needs >= 128 MiB of input (the reference shrinks the window to the file): 140 MB of
+    long-range data in two blocks; every step must be a true in-window match, strictly increasing."""
+    from nlzm_b200 import synth
+    from nlzm_b200.matchfinder import MatchFinders, geometry
+    x = synth.longrange(140_000_000, 77)
+    assert geometry(x.size, 28, cuda_lib).hist_bits == 28
+    with MatchFinders(cuda_lib) as mf:
+        mf.Init(28, x, max_range=1 << 27)
+        total = 0
+        for i, (b, e) in enumerate([(0, 1 << 26), (1 << 26, x.size)]):
+            off, st = mf.FindAndUpdate(b, e, slot=i, copy=False)
+            _check_properties(x, off, st, b, 1 << 28)
+            total += st.size
+    assert total > x.size          # redundant data: several steps per position
