@@ -112,6 +112,11 @@ int nlzm_mf_fetch(nlzm_mf *mf, int slot, nlzm_mf_view *out);                    
 
 int nlzm_mf_get_stats(const nlzm_mf *mf, nlzm_mf_stats *out);
 
+/* Tuning / test knobs (no reference counterpart; results never depend on them):
+ *   "ht_margin"      positions before a range for which the HT stage materialises per-position data (default 4 Mi)
+ *   "ht_coarse_log"  log2 of the coarse table spacing of the far prefix (default 20) */
+int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value);
+
 /* Measurement aid (no reference counterpart): with profiling enabled every kernel launch is
  * bracketed by CUDA events on its stream and accumulated per kernel name (process wide). */
 typedef struct {

@@ -39,7 +39,7 @@ class KernelTime(C.Structure):
     _fields_ = [("name", C.c_char * 56), ("launches", C.c_uint64), ("ms", C.c_double)]
 
 
-EXPORTS = ["nlzm_mf_profile", "nlzm_mf_get_kernel_times", "nlzm_mf_abi_version", "nlzm_mf_get_geometry", "nlzm_mf_create", "nlzm_mf_destroy",
+EXPORTS = ["nlzm_mf_set_option", "nlzm_mf_profile", "nlzm_mf_get_kernel_times", "nlzm_mf_abi_version", "nlzm_mf_get_geometry", "nlzm_mf_create", "nlzm_mf_destroy",
            "nlzm_mf_last_error", "nlzm_mf_set_input", "nlzm_mf_set_input_device", "nlzm_mf_find",
            "nlzm_mf_find_device", "nlzm_mf_submit", "nlzm_mf_fetch", "nlzm_mf_get_stats"]
 
@@ -60,6 +60,7 @@ def bind_prototypes(L):
     L.nlzm_mf_submit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
     L.nlzm_mf_fetch.argtypes = [C.c_void_p, C.c_int, C.POINTER(View)]
     L.nlzm_mf_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.nlzm_mf_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
     L.nlzm_mf_profile.argtypes = [C.c_int]
     L.nlzm_mf_get_kernel_times.argtypes = [C.POINTER(KernelTime), C.c_uint32, C.POINTER(C.c_uint32)]
     return L

@@ -14,7 +14,11 @@
 //   k_ht_find        per position: resolve the raw cell contents (a short chain when the last writer
 //                    pushed an older entry), then the reference's match / check-bit / window logic
 // MatchFinderHT::Shift as written only clears cell 0 at each ring shift (NLZM.cpp:940-957); tables
-// never age, so PS/PL/PR are built over the whole prefix [0, end) — streaming work, no sort.
+// never age, so the last-access tables cover the whole prefix [0, end) — streaming work, no sort.
+// PS/PL/PR themselves are only materialised from `pos0` = a few MiB before the answered range (a
+// chain almost never reaches further back: the last writer of a cell is recent); for the far prefix
+// there is one coarse table per 1 Mi positions, and the rare chain step that lands there scans back
+// to the start of its coarse tile and then takes the table value (exact, see ht_last_before).
 #pragma once
 #include "common.cuh"
 #include "dc_levels.cuh"
@@ -25,7 +29,10 @@ struct HtCfg {
     u32 nbytes;    // 2 or 3 hashed bytes
 };
 
-#define NLZM_HT_TILE 65536u
+#define NLZM_HT_TILE_LOG 16u                   // fine tiles: k_ht_prev walks these in order
+#define NLZM_HT_TILE (1u << NLZM_HT_TILE_LOG)
+#define NLZM_HT_COARSE_LOG 20u                 // coarse tiles of the far prefix
+#define NLZM_HT_MARGIN (4u << 20)              // PS/PL/PR start this far before the answered range
 #define NLZM_HT_THREADS 256
 #define NLZM_HT_STAGE 2048u                     // text bytes staged in shared memory by k_ht_prev
 
@@ -37,11 +44,15 @@ HD u32 ht_hash(const u8 *__restrict__ x, u64 a, u32 nbytes) {
 struct HtTableParams {
     const u8 *x;
     HtCfg c;
-    u64 n_acc;        // accesses happen at positions [0, n_acc) (4 bytes visible, NLZM.cpp:1515)
+    u64 pos0;         // first position the tiles of this launch cover (multiple of the tile size)
+    u64 n_acc;        // accesses happen at positions [0, n_acc) (4 bytes visible, NLZM.cpp:1515); tiles end here
     u64 x_limit;      // 8-byte words may be read at offsets <= x_limit (input length + padding - 8)
+    u32 tile_log;     // log2 of the tile size of this launch
     u32 n_tiles;
     u32 *tile_last;   // [n_tiles][1 << bits]: last access (+1) per bucket inside the tile, then: before the tile
-    u32 *ps, *pl, *pr;// per position: last access (+1, 0 = none) before it in bucket b, b-1, b+1
+    const u32 *init;  // table before the first tile (1 << bits entries) or null = empty
+    u32 *final_row;   // out: table after the last tile (or null)
+    u32 *ps, *pl, *pr;// per position - pos0: last access (+1, 0 = none) before it in bucket b, b-1, b+1
 };
 
 // ---- per tile: last access per bucket
@@ -50,8 +61,8 @@ DEV void ht_tile_last_cta(const HtTableParams &p, u32 bid, u32 tid, u8 *smem) {
     const u32 nc = 1u << p.c.bits;
     for (u32 i = tid; i < nc; i += NLZM_HT_THREADS) tab[i] = 0;
     NLZM_CTA_SYNC();
-    const u64 t0 = (u64)bid * NLZM_HT_TILE;
-    const u64 t1 = t0 + NLZM_HT_TILE < p.n_acc ? t0 + NLZM_HT_TILE : p.n_acc;
+    const u64 t0 = p.pos0 + ((u64)bid << p.tile_log);
+    const u64 t1 = t0 + (1ull << p.tile_log) < p.n_acc ? t0 + (1ull << p.tile_log) : p.n_acc;
     for (u64 a = t0 + tid; a < t1; a += NLZM_HT_THREADS)
         nlzm_atomic_max(tab + (ht_hash(p.x, a, p.c.nbytes) >> (32 - p.c.bits)), (u32)a + 1u);
     NLZM_CTA_SYNC();
@@ -63,13 +74,14 @@ NLZM_KERNEL_CTA(ht_tile_last, HtTableParams, NLZM_HT_THREADS)
 // ---- exclusive running max over tiles (one thread per bucket, coalesced across buckets)
 DEV void ht_tile_scan_body(const HtTableParams &p, u64 b) {
     const u32 nc = 1u << p.c.bits;
-    u32 run = 0;
+    u32 run = p.init ? p.init[b] : 0u;
     for (u32 t = 0; t < p.n_tiles; t++) {
         u32 *cell = p.tile_last + (u64)t * nc + b;
         const u32 v = *cell;
         *cell = run;
         run = v > run ? v : run;
     }
+    if (p.final_row) p.final_row[b] = run;
 }
 NLZM_KERNEL_1D(ht_tile_scan, HtTableParams)
 
@@ -82,7 +94,7 @@ __global__ void __launch_bounds__(32) k_ht_prev(const HtTableParams p) {
     const u32 *init = p.tile_last + (u64)blockIdx.x * nc;
     for (u32 i = lane; i < nc; i += 32) tab[i] = init[i];
     __syncwarp();
-    const u64 t0 = (u64)blockIdx.x * NLZM_HT_TILE;
+    const u64 t0 = p.pos0 + (u64)blockIdx.x * NLZM_HT_TILE;
     const u64 t1 = t0 + NLZM_HT_TILE < p.n_acc ? t0 + NLZM_HT_TILE : p.n_acc;
     const u32 shift = 32 - p.c.bits;
     const u32 vmask = p.c.nbytes == 2 ? 0xFFFFu : 0xFFFFFFu;
@@ -143,8 +155,8 @@ __global__ void __launch_bounds__(32) k_ht_prev(const HtTableParams p) {
             }
         }
         if (live) {
-            p.ps[a] = vs;
-            if (p.c.rows == 2) { p.pl[a] = vl; p.pr[a] = vr; }
+            p.ps[a - p.pos0] = vs;
+            if (p.c.rows == 2) { p.pl[a - p.pos0] = vl; p.pr[a - p.pos0] = vr; }
         }
         __syncwarp();
     }
@@ -170,11 +182,11 @@ static inline int launch_ht_prev(const HtTableParams &p, u64 grid, size_t, cudaS
     std::vector<u32> tab(nc);
     for (u64 t = 0; t < grid; t++) {
         for (u32 i = 0; i < nc; i++) tab[i] = p.tile_last[t * nc + i];
-        const u64 t0 = t * NLZM_HT_TILE, t1 = t0 + NLZM_HT_TILE < p.n_acc ? t0 + NLZM_HT_TILE : p.n_acc;
+        const u64 t0 = p.pos0 + t * NLZM_HT_TILE, t1 = t0 + NLZM_HT_TILE < p.n_acc ? t0 + NLZM_HT_TILE : p.n_acc;
         for (u64 a = t0; a < t1; a++) {
             const u32 b = ht_hash(p.x, a, p.c.nbytes) >> shift;
-            p.ps[a] = tab[b];
-            if (p.c.rows == 2) { p.pl[a] = b > 0 ? tab[b - 1] : 0; p.pr[a] = b + 1 < nc ? tab[b + 1] : 0; }
+            p.ps[a - p.pos0] = tab[b];
+            if (p.c.rows == 2) { p.pl[a - p.pos0] = b > 0 ? tab[b - 1] : 0; p.pr[a - p.pos0] = b + 1 < nc ? tab[b + 1] : 0; }
             tab[b] = (u32)a + 1u;
         }
     }
@@ -187,7 +199,10 @@ struct HtFindParams {
     const u8 *x;
     Geom g;
     HtCfg c;
-    const u32 *ps, *pl, *pr;
+    const u32 *ps, *pl, *pr;   // indexed by position - pos0
+    u64 pos0;                  // first position PS/PL/PR exist for
+    const u32 *coarse;         // [pos0 >> coarse_log][1 << bits]: table before each coarse tile of the far prefix
+    u32 coarse_log;
     u64 own_b;
     u32 bt_on;           // exhaustive BT4 runs too: it reports a candidate at least as near and as long for every
                          // match of 4+ bytes, so those need not be queued twice (they would be merged away)
@@ -199,6 +214,18 @@ DEV u32 ht_entry(const HtFindParams &p, u64 w) {
     const u32 cmask = (1u << (32 - p.g.hb)) - 1;
     return geom_P(p.g, w) | ((ht_hash(p.x, w, p.c.nbytes) & cmask) << p.g.hb);
 }
+
+// last access (+1, 0 = none) before position q in `bucket`, for q in the far prefix: scan back to the start
+// of q's coarse tile, then the coarse table (which holds the last access before that tile)
+DEV u32 ht_last_before(const HtFindParams &p, u32 bucket, u64 q) {
+    const u64 tile = q >> p.coarse_log, t0 = tile << p.coarse_log;
+    const u32 shift = 32 - p.c.bits;
+    for (u64 a = q; a-- > t0; )
+        if ((ht_hash(p.x, a, p.c.nbytes) >> shift) == bucket) return (u32)a + 1u;
+    return p.coarse[tile * ((u64)1 << p.c.bits) + bucket];
+}
+DEV u32 ht_ps(const HtFindParams &p, u64 q, u32 bucket) { return q >= p.pos0 ? p.ps[q - p.pos0] : ht_last_before(p, bucket, q); }
+DEV u32 ht_pl(const HtFindParams &p, u64 q, u32 bucket) { return q >= p.pos0 ? p.pl[q - p.pos0] : ht_last_before(p, bucket - 1, q); }
 
 // raw u32 content of cell `cell` as seen by a reader at time t, given the last accesses (+1) before t
 // of bucket `cell` (w0: writes its own entry) and of bucket `cell - 1` (w1: pushes cell-1's old content)
@@ -213,9 +240,9 @@ DEV u32 ht_cell_value(const HtFindParams &p, u32 cell, u64 t, u32 w0, u32 w1) {
         if (w0 > w1) return ht_entry(p, w0 - 1);
         const u64 q = w1 - 1;                 // bucket cell-1 accessed at q and pushed the old content of cell-1
         t = q;
-        cell -= 1;
-        w0 = p.ps[q];
-        w1 = (p.c.rows == 2 && cell > 0) ? p.pl[q] : 0u;
+        cell -= 1;                            // = q's bucket
+        w0 = ht_ps(p, q, cell);
+        w1 = (p.c.rows == 2 && cell > 0) ? ht_pl(p, q, cell) : 0u;
     }
 }
 
@@ -229,11 +256,12 @@ DEV void ht_find_body(const HtFindParams &p, u64 i) {
     const u32 rem = geom_rem(p.g, a);
     const u32 cap = rem < NLZM_MATCH_MAX ? rem : NLZM_MATCH_MAX;      // NLZM.cpp:915
     const u64 base = a - P;
-    const u32 ps = p.ps[a];
+    const u64 ai = a - p.pos0;
+    const u32 ps = p.ps[ai];
     u32 best = 1;                                                     // MATCH_MIN - 1, NLZM.cpp:917
     for (u32 r = 0; r < p.c.rows; r++) {
-        const u32 row = r == 0 ? ht_cell_value(p, b, a, ps, (p.c.rows == 2 && b > 0) ? p.pl[a] : 0u)
-                               : ht_cell_value(p, b + 1, a, p.pr[a], ps);
+        const u32 row = r == 0 ? ht_cell_value(p, b, a, ps, (p.c.rows == 2 && b > 0) ? p.pl[ai] : 0u)
+                               : ht_cell_value(p, b + 1, a, p.pr[ai], ps);
         if (best < cap && (row >> p.g.hb) == chk) {
             const u32 sp = row & (p.g.W - 1);
             if (sp < P && P - sp <= p.g.W - 1) {

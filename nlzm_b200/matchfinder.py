@@ -95,6 +95,10 @@ class MatchFinders:
         self._check(self._L.nlzm_mf_fetch(self._h, slot, C.byref(v)), "fetch")
         return self._view_to_numpy(v, copy)
 
+    def set_option(self, key: str, value: int) -> None:
+        """tuning / test knobs, see nlzm_mf_set_option in include/nlzm_mf.h"""
+        self._check(self._L.nlzm_mf_set_option(self._h, key.encode(), value), "set_option")
+
     def stats(self) -> _lib.Stats:
         s = _lib.Stats()
         self._L.nlzm_mf_get_stats(self._h, C.byref(s))

@@ -61,6 +61,29 @@ def test_emu_tiny(emu_lib, orc, n):
     assert orc.csr_equal(ref, _run(emu_lib, x, 15))
 
 
+def test_emu_ht_far_prefix(emu_lib, orc):
+    """HT stage with a tiny margin: chains of later ranges must fall back to the coarse prefix tables"""
+    from nlzm_b200 import synth
+    from nlzm_b200.matchfinder import MatchFinders
+    x = synth.mixed(150_000, 33)
+    for hb, mask in ((15, 3), (16, 3)):
+        ref = orc.find(x, hb, mask)
+        with MatchFinders(emu_lib) as mf:
+            mf.Init(hb, x, finder_mask=mask)
+            mf.set_option("ht_margin", 0)
+            mf.set_option("ht_coarse_log", 11)
+            offs, ds, ls, base = [np.zeros(1, np.uint64)], [], [], 0
+            cuts = [0, 50_000, 100_001, x.size]
+            for i, (b, e) in enumerate(zip(cuts[:-1], cuts[1:])):
+                off, st = mf.FindAndUpdate(b, e, slot=i & 1)
+                offs.append(off[1:].astype(np.uint64) + base)
+                base += int(off[-1])
+                ds.append(st["dist"].copy())
+                ls.append(st["len"].copy())
+        got = (np.concatenate(offs), np.concatenate(ds), np.concatenate(ls))
+        assert orc.csr_equal(ref, got), (hb, orc.first_diff(ref, got))
+
+
 def test_emu_golden(emu_lib, orc):
     """committed fixtures that came from the reference's real encoder"""
     import glob, os

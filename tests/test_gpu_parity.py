@@ -66,6 +66,29 @@ def test_tiny_inputs(cuda_lib, orc, n):
     assert orc.csr_equal(ref, got)
 
 
+def test_ht_far_prefix_tables(cuda_lib, orc):
+    """later ranges with a tiny HT margin: chains fall back to the coarse prefix tables (exact)"""
+    from nlzm_b200 import synth
+    from nlzm_b200.matchfinder import MatchFinders
+    x = np.concatenate([synth.mixed(500_000, 33), synth.text(500_000, 34)])
+    for hb in (15, 24):
+        ref = orc.find(x, hb, 3)
+        with MatchFinders(cuda_lib) as mf:
+            mf.Init(hb, x, finder_mask=3)
+            mf.set_option("ht_margin", 0)
+            mf.set_option("ht_coarse_log", 12)
+            offs, ds, ls, base = [np.zeros(1, np.uint64)], [], [], 0
+            cuts = [0, 300_000, 700_001, x.size]
+            for i, (b, e) in enumerate(zip(cuts[:-1], cuts[1:])):
+                off, st = mf.FindAndUpdate(b, e, slot=i & 1)
+                offs.append(off[1:].astype(np.uint64) + base)
+                base += int(off[-1])
+                ds.append(st["dist"].copy())
+                ls.append(st["len"].copy())
+        got = (np.concatenate(offs), np.concatenate(ds), np.concatenate(ls))
+        assert orc.csr_equal(ref, got), (hb, orc.first_diff(ref, got))
+
+
 def test_submit_fetch_pipeline(cuda_lib, orc):
     from nlzm_b200 import synth
     from nlzm_b200.matchfinder import MatchFinders
