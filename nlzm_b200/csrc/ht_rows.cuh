@@ -7,18 +7,22 @@
 // and of bucket c-1 (the pushed old content of cell c-1). So everything follows from three numbers
 // per position p with bucket b:  PS[p], PL[p], PR[p] = the last access before p in bucket b, b-1,
 // b+1. They are computed with per-tile "last access" tables:
-//   k_ht_tile_last   per tile of 64 Ki positions: last access per bucket (shared-memory atomicMax)
-//   k_ht_tile_scan   exclusive running max over the tiles, per bucket  => table at every tile start
-//   k_ht_prev        per tile, in position order: one warp walks the tile 32 positions at a time with
-//                    the table in shared memory; accesses inside the same 32 are resolved with shuffles
+//   k_ht_tile_last   per tile of 32 Ki positions: last access per bucket (shared-memory atomicMax)
+//   k_ht_scan_*      exclusive running max over the tiles, per bucket, in two levels (groups of 64 tiles)
+//                    => table at every tile start
+//   k_ht_prev        per tile, in position order: one warp walks the tile 32 positions at a time with a
+//                    u16 table (in-tile offsets) and 2 KiB of staged text in shared memory; accesses
+//                    inside the same 32 are resolved from the __match_any mask and the table itself,
+//                    with 31 shuffles only when a later lane touched a neighbouring bucket
 //   k_ht_find        per position: resolve the raw cell contents (a short chain when the last writer
 //                    pushed an older entry), then the reference's match / check-bit / window logic
 // MatchFinderHT::Shift as written only clears cell 0 at each ring shift (NLZM.cpp:940-957); tables
 // never age, so the last-access tables cover the whole prefix [0, end) — streaming work, no sort.
-// PS/PL/PR themselves are only materialised from `pos0` = a few MiB before the answered range (a
-// chain almost never reaches further back: the last writer of a cell is recent); for the far prefix
-// there is one coarse table per 1 Mi positions, and the rare chain step that lands there scans back
-// to the start of its coarse tile and then takes the table value (exact, see ht_last_before).
+// PS/PL/PR are materialised from `pos0` on: by default 0 (whole prefix, 12 B per position). With the
+// "ht_margin" option they start that far before the answered range and the far prefix only gets one
+// coarse table per 2^ht_coarse_log positions; a chain step that lands there is resolved exactly from
+// the coarse tables, scanning text only when it falls between two accesses of one coarse tile
+// (measured on a late shard of 800 MB text: the scans cost far more than the 12 B per position save).
 #pragma once
 #include "common.cuh"
 #include "dc_levels.cuh"
@@ -29,10 +33,13 @@ struct HtCfg {
     u32 nbytes;    // 2 or 3 hashed bytes
 };
 
-#define NLZM_HT_TILE_LOG 16u                   // fine tiles: k_ht_prev walks these in order
+#define NLZM_HT_TILE_LOG 15u                   // fine tiles: k_ht_prev walks these in order (in-tile offsets fit u16)
+#define NLZM_HT_GROUP 64u                      // tiles per group of the two-level running max
 #define NLZM_HT_TILE (1u << NLZM_HT_TILE_LOG)
 #define NLZM_HT_COARSE_LOG 20u                 // coarse tiles of the far prefix
-#define NLZM_HT_MARGIN (4u << 20)              // PS/PL/PR start this far before the answered range
+#define NLZM_HT_MARGIN 0xFFFFFFFFFFFFull        // PS/PL/PR start this far before the answered range: by default the
+                                               // whole prefix (12 B per position); a smaller margin (option "ht_margin")
+                                               // trades memory for slow exact look-ups in the far prefix
 #define NLZM_HT_THREADS 256
 #define NLZM_HT_STAGE 2048u                     // text bytes staged in shared memory by k_ht_prev
 
@@ -50,8 +57,8 @@ struct HtTableParams {
     u32 tile_log;     // log2 of the tile size of this launch
     u32 n_tiles;
     u32 *tile_last;   // [n_tiles][1 << bits]: last access (+1) per bucket inside the tile, then: before the tile
-    const u32 *init;  // table before the first tile (1 << bits entries) or null = empty
-    u32 *final_row;   // out: table after the last tile (or null)
+    u32 *first_rows;  // out (coarse launch only, else null): [n_tiles][1 << bits] first access (+1) inside the tile
+    u32 *last_rows;   // out (coarse launch only): copy of the per-tile last access before the scan overwrites it
     u32 *ps, *pl, *pr;// per position - pos0: last access (+1, 0 = none) before it in bucket b, b-1, b+1
 };
 
@@ -59,46 +66,92 @@ struct HtTableParams {
 DEV void ht_tile_last_cta(const HtTableParams &p, u32 bid, u32 tid, u8 *smem) {
     u32 *tab = (u32 *)smem;
     const u32 nc = 1u << p.c.bits;
-    for (u32 i = tid; i < nc; i += NLZM_HT_THREADS) tab[i] = 0;
+    u32 *tmin = tab + nc;                                        // only with first_rows (launcher sizes the memory)
+    for (u32 i = tid; i < nc; i += NLZM_HT_THREADS) { tab[i] = 0; if (p.first_rows) tmin[i] = 0xFFFFFFFFu; }
     NLZM_CTA_SYNC();
     const u64 t0 = p.pos0 + ((u64)bid << p.tile_log);
     const u64 t1 = t0 + (1ull << p.tile_log) < p.n_acc ? t0 + (1ull << p.tile_log) : p.n_acc;
-    for (u64 a = t0 + tid; a < t1; a += NLZM_HT_THREADS)
-        nlzm_atomic_max(tab + (ht_hash(p.x, a, p.c.nbytes) >> (32 - p.c.bits)), (u32)a + 1u);
+    for (u64 a = t0 + tid; a < t1; a += NLZM_HT_THREADS) {
+        const u32 b = ht_hash(p.x, a, p.c.nbytes) >> (32 - p.c.bits);
+        nlzm_atomic_max(tab + b, (u32)a + 1u);
+        if (p.first_rows) nlzm_atomic_min(tmin + b, (u32)a + 1u);
+    }
     NLZM_CTA_SYNC();
     u32 *out = p.tile_last + (u64)bid * nc;
-    for (u32 i = tid; i < nc; i += NLZM_HT_THREADS) out[i] = tab[i];
+    for (u32 i = tid; i < nc; i += NLZM_HT_THREADS) {
+        out[i] = tab[i];
+        if (p.first_rows) {
+            p.last_rows[(u64)bid * nc + i] = tab[i];
+            p.first_rows[(u64)bid * nc + i] = tmin[i] == 0xFFFFFFFFu ? 0u : tmin[i];
+        }
+    }
 }
 NLZM_KERNEL_CTA(ht_tile_last, HtTableParams, NLZM_HT_THREADS)
 
-// ---- exclusive running max over tiles (one thread per bucket, coalesced across buckets)
-DEV void ht_tile_scan_body(const HtTableParams &p, u64 b) {
-    const u32 nc = 1u << p.c.bits;
+// ---- exclusive running max over the tiles, per bucket, in two levels so that long prefixes stay parallel:
+//      group maxima -> running max over groups -> running max inside each group
+struct HtScanParams {
+    u32 *tile_last;     // [n_tiles][nc], converted in place to "table before the tile"
+    u32 *group_max;     // [n_groups][nc] scratch
+    const u32 *init;    // table before the first tile, or null
+    u32 *final_row;     // out: table after the last tile, or null
+    u32 nc, n_tiles, n_groups;
+};
+DEV void ht_scan_group_body(const HtScanParams &p, u64 i) {         // i = group * nc + bucket
+    const u32 g = (u32)(i / p.nc), b = (u32)(i % p.nc);
+    const u32 t1 = (g + 1) * NLZM_HT_GROUP < p.n_tiles ? (g + 1) * NLZM_HT_GROUP : p.n_tiles;
+    u32 m = 0;
+    for (u32 t = g * NLZM_HT_GROUP; t < t1; t++) { const u32 v = p.tile_last[(u64)t * p.nc + b]; m = v > m ? v : m; }
+    p.group_max[i] = m;
+}
+NLZM_KERNEL_1D(ht_scan_group, HtScanParams)
+DEV void ht_scan_top_body(const HtScanParams &p, u64 b) {           // one thread per bucket over the groups
     u32 run = p.init ? p.init[b] : 0u;
-    for (u32 t = 0; t < p.n_tiles; t++) {
-        u32 *cell = p.tile_last + (u64)t * nc + b;
+    for (u32 g = 0; g < p.n_groups; g++) {
+        u32 *cell = p.group_max + (u64)g * p.nc + b;
         const u32 v = *cell;
         *cell = run;
         run = v > run ? v : run;
     }
     if (p.final_row) p.final_row[b] = run;
 }
-NLZM_KERNEL_1D(ht_tile_scan, HtTableParams)
+NLZM_KERNEL_1D(ht_scan_top, HtScanParams)
+DEV void ht_scan_apply_body(const HtScanParams &p, u64 i) {
+    const u32 g = (u32)(i / p.nc), b = (u32)(i % p.nc);
+    const u32 t1 = (g + 1) * NLZM_HT_GROUP < p.n_tiles ? (g + 1) * NLZM_HT_GROUP : p.n_tiles;
+    u32 run = p.group_max[i];
+    for (u32 t = g * NLZM_HT_GROUP; t < t1; t++) {
+        u32 *cell = p.tile_last + (u64)t * p.nc + b;
+        const u32 v = *cell;
+        *cell = run;
+        run = v > run ? v : run;
+    }
+}
+NLZM_KERNEL_1D(ht_scan_apply, HtScanParams)
+static inline void launch_ht_tile_scan(const HtScanParams &p, cudaStream_t st) {
+    launch_ht_scan_group(p, (u64)p.n_groups * p.nc, st);
+    launch_ht_scan_top(p, p.nc, st);
+    launch_ht_scan_apply(p, (u64)p.n_groups * p.nc, st);
+}
 
 // ---- per tile, in position order: PS / PL / PR
 #if !defined(NLZM_EMU)
+// shared table: in-tile offset + 1 of the bucket's last access (u16, 0 = not accessed in this tile yet, then the
+// value comes from the table before the tile in global memory). Half the footprint of absolute positions
+// => twice the resident warps of this latency-bound walk.
 __global__ void __launch_bounds__(32) k_ht_prev(const HtTableParams p) {
     extern __shared__ __align__(16) u8 nlzm_smem[];
-    u32 *tab = (u32 *)nlzm_smem;
+    u16 *tab = (u16 *)nlzm_smem;
     const u32 nc = 1u << p.c.bits, lane = threadIdx.x;
-    const u32 *init = p.tile_last + (u64)blockIdx.x * nc;
-    for (u32 i = lane; i < nc; i += 32) tab[i] = init[i];
-    __syncwarp();
+    const u32 *__restrict__ init = p.tile_last + (u64)blockIdx.x * nc;
+    for (u32 i = lane; i < nc; i += 32) tab[i] = 0;
     const u64 t0 = p.pos0 + (u64)blockIdx.x * NLZM_HT_TILE;
     const u64 t1 = t0 + NLZM_HT_TILE < p.n_acc ? t0 + NLZM_HT_TILE : p.n_acc;
+    const u32 t0p = (u32)t0;
     const u32 shift = 32 - p.c.bits;
     const u32 vmask = p.c.nbytes == 2 ? 0xFFFFu : 0xFFFFFFu;
-    u32 *stage = tab + nc;                         // NLZM_HT_STAGE + 8 text bytes of the walk, refilled every 64 steps
+    u32 *stage = (u32 *)(nlzm_smem + (size_t)nc * 2);      // NLZM_HT_STAGE + 8 text bytes of the walk, refilled every 64 steps
+    __syncwarp();
     for (u64 base = t0; base < t1; base += 32) {
         const u32 in_stage = (u32)(base - t0) & (NLZM_HT_STAGE - 1);
         if (in_stage == 0) {
@@ -121,34 +174,38 @@ __global__ void __launch_bounds__(32) k_ht_prev(const HtTableParams p) {
         }
         u32 vs = 0, vl = 0, vr = 0;
         if (live) {
-            vs = tab[b];
+            u32 v = tab[b];
+            vs = v ? t0p + v : init[b];
             if (p.c.rows == 2) {
-                if (b > 0) vl = tab[b - 1];
-                if (b + 1 < nc) vr = tab[b + 1];
+                if (b > 0) { v = tab[b - 1]; vl = v ? t0p + v : init[b - 1]; }
+                if (b + 1 < nc) { v = tab[b + 1]; vr = v ? t0p + v : init[b + 1]; }
             }
         }
-        // Every lane publishes its access; if nobody else's shows up in the three cells a lane looks at,
-        // the 32 accesses do not interact (the common case) and the values read above are final.
+        // The last access of each bucket among these 32 goes into the table (one writer per bucket); if no
+        // lane shares a bucket and nobody else's access shows up in the cells a lane looks at, the 32
+        // accesses do not interact (the common case) and the values read above are final.
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, b);
         __syncwarp();                                                    // all lanes have read the pre-step table
-        if (live) atomicMax(&tab[b], (u32)a + 1u);                       // the last access of a bucket wins
+        const u32 me = (u32)(a - t0) + 1u;
+        if (live && (peers >> lane) == 1u) tab[b] = (u16)me;
         __syncwarp();
-        bool clash = false;
-        if (live) {
-            const u32 lo = (u32)base, me = (u32)a + 1u;
-            const u32 cs = tab[b];
-            clash = cs != me;                                            // another lane has my bucket
-            if (p.c.rows == 2) {
-                if (b > 0) { const u32 v = tab[b - 1]; clash |= v > lo; }       // a lane of this step accessed bucket b-1
-                if (b + 1 < nc) { const u32 v = tab[b + 1]; clash |= v > lo; }
-            }
+        // Same bucket in a lower lane: the nearest one is the predecessor (exact, from the match mask).
+        const unsigned lower = peers & ((1u << lane) - 1u);
+        if (live && lower) vs = (u32)base + (31u - (u32)__clz((int)lower)) + 1u;
+        // Neighbour buckets: the table now holds the LAST lane of each bucket touched in this step. If that lane
+        // is below me it is my predecessor; if it is above me, a lower one may exist as well: rare, settled below.
+        bool redo = false;
+        if (live && p.c.rows == 2) {
+            const u32 lo = (u32)(base - t0);
+            if (b > 0) { const u32 t = tab[b - 1]; if (t > lo) { const u32 j = t - 1u - lo; if (j < lane) vl = (u32)base + j + 1u; else redo = true; } }
+            if (b + 1 < nc) { const u32 t = tab[b + 1]; if (t > lo) { const u32 j = t - 1u - lo; if (j < lane) vr = (u32)base + j + 1u; else redo = true; } }
         }
-        if (__any_sync(0xFFFFFFFFu, clash)) {
+        if (__any_sync(0xFFFFFFFFu, redo)) {
             // accesses inside these 32 positions, in order: a later lane overrides an earlier one
             for (u32 j = 0; j < 31; j++) {
                 const u32 bj = __shfl_sync(0xFFFFFFFFu, b, j);
                 if (j < lane) {
                     const u32 pj = (u32)(base + j) + 1u;
-                    if (bj == b) vs = pj;
                     if (bj + 1 == b) vl = pj;
                     if (bj == b + 1) vr = pj;
                 }
@@ -202,6 +259,8 @@ struct HtFindParams {
     const u32 *ps, *pl, *pr;   // indexed by position - pos0
     u64 pos0;                  // first position PS/PL/PR exist for
     const u32 *coarse;         // [pos0 >> coarse_log][1 << bits]: table before each coarse tile of the far prefix
+    const u32 *coarse_first;   // same shape: first access (+1) inside the coarse tile, 0 = none
+    const u32 *coarse_last;    // same shape: last access (+1) inside the coarse tile, 0 = none
     u32 coarse_log;
     u64 own_b;
     u32 bt_on;           // exhaustive BT4 runs too: it reports a candidate at least as near and as long for every
@@ -219,10 +278,15 @@ DEV u32 ht_entry(const HtFindParams &p, u64 w) {
 // of q's coarse tile, then the coarse table (which holds the last access before that tile)
 DEV u32 ht_last_before(const HtFindParams &p, u32 bucket, u64 q) {
     const u64 tile = q >> p.coarse_log, t0 = tile << p.coarse_log;
-    const u32 shift = 32 - p.c.bits;
+    const u64 cell = tile * ((u64)1 << p.c.bits) + bucket;
+    const u32 first = p.coarse_first[cell];
+    if (first == 0 || (u64)first - 1 >= q) return p.coarse[cell];      // no access of this bucket in [t0, q)
+    const u32 last = p.coarse_last[cell];
+    if ((u64)last - 1 < q) return last;                                 // the tile's last access lies before q
+    const u32 shift = 32 - p.c.bits;                                    // q sits between accesses of its tile: scan back
     for (u64 a = q; a-- > t0; )
         if ((ht_hash(p.x, a, p.c.nbytes) >> shift) == bucket) return (u32)a + 1u;
-    return p.coarse[tile * ((u64)1 << p.c.bits) + bucket];
+    return p.coarse[cell];
 }
 DEV u32 ht_ps(const HtFindParams &p, u64 q, u32 bucket) { return q >= p.pos0 ? p.ps[q - p.pos0] : ht_last_before(p, bucket, q); }
 DEV u32 ht_pl(const HtFindParams &p, u64 q, u32 bucket) { return q >= p.pos0 ? p.pl[q - p.pos0] : ht_last_before(p, bucket - 1, q); }

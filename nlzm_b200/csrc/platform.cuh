@@ -54,6 +54,7 @@ typedef int64_t i64;
 DEV u32 nlzm_atomic_add(u32 *p, u32 v) { return atomicAdd(p, v); }
 DEV u64 nlzm_atomic_add64(unsigned long long *p, u64 v) { return atomicAdd(p, (unsigned long long)v); }
 DEV u32 nlzm_atomic_max(u32 *p, u32 v) { return atomicMax(p, v); }
+DEV u32 nlzm_atomic_min(u32 *p, u32 v) { return atomicMin(p, v); }
 HD int nlzm_ctz64(u64 v) {
 #ifdef __CUDA_ARCH__
     return __ffsll((long long)v) - 1;
@@ -112,6 +113,11 @@ static inline u64 nlzm_atomic_add64(unsigned long long *p, u64 v) { return __ato
 static inline u32 nlzm_atomic_max(u32 *p, u32 v) {
     u32 o = __atomic_load_n(p, __ATOMIC_RELAXED);
     while (v > o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return o;
+}
+static inline u32 nlzm_atomic_min(u32 *p, u32 v) {
+    u32 o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < o && !__atomic_compare_exchange_n(p, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
     return o;
 }
 static inline int nlzm_ctz64(u64 v) { return __builtin_ctzll(v); }
