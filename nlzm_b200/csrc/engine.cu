@@ -18,6 +18,7 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <new>
 #include <string>
 #include <thread>
 #include <vector>
@@ -618,7 +619,8 @@ int nlzm_mf_create(const nlzm_mf_config *cfg, nlzm_mf **out) {
     if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "bad device ordinal"; return NLZM_MF_E_ARG; }
     cudaSetDevice(cfg->device);
 #endif
-    nlzm_mf *mf = new nlzm_mf();
+    nlzm_mf *mf = new (std::nothrow) nlzm_mf();
+    if (!mf) { g_create_error = "out of host memory"; return NLZM_MF_E_NOMEM; }
     mf->g = make_geom(cfg->file_len, cfg->hist_bits);
     mf->device = cfg->device;
     mf->mask = cfg->finder_mask ? cfg->finder_mask : (u32)NLZM_MF_ALL;
@@ -707,8 +709,12 @@ int nlzm_mf_submit(nlzm_mf *mf, uint64_t begin, uint64_t end, int slot) {
     Slot &s = mf->slot[slot];
     if (s.pending) return mf->fail(NLZM_MF_E_STATE, "slot already has a pending submit");
     if (s.worker.joinable()) s.worker.join();
+    try {
+        s.worker = std::thread([mf, begin, end, slot]() { mf->slot[slot].status = mf->find_impl(begin, end, slot, true); });
+    } catch (const std::exception &ex) {
+        return mf->fail(NLZM_MF_E_NOMEM, std::string("cannot start the submit thread: ") + ex.what());
+    }
     s.pending = true;
-    s.worker = std::thread([mf, begin, end, slot]() { mf->slot[slot].status = mf->find_impl(begin, end, slot, true); });
     return 0;
 }
 
