@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NLZM_MF_ABI_VERSION 1
+#define NLZM_MF_ABI_VERSION 2
 
 enum nlzm_mf_finder {
     NLZM_MF_HT2 = 1,      /* MatchFinderHT, 2-byte hash, 1 row   (NLZM.cpp:1750) */
@@ -70,12 +70,13 @@ typedef struct {
     uint32_t ht2_bits, ht3_bits, bt4_bits, rk_bits;
 } nlzm_mf_geometry;
 
-/* One staircase step == one MatchTable::Update(dist, len). */
+/* One staircase step == one MatchTable::Update(dist, len). Six bytes (three u16, no padding): the
+ * candidate records are what crosses PCIe, 3.5 of them per input byte on text. */
 typedef struct {
-    uint32_t dist;
+    uint16_t dist_lo, dist_hi;     /* distance = dist_lo | dist_hi << 16 */
     uint16_t len;
-    uint16_t reserved;
 } nlzm_mf_step;
+#define NLZM_MF_STEP_DIST(s) ((uint32_t)(s).dist_lo | ((uint32_t)(s).dist_hi << 16))
 
 /* Candidates of positions [begin, end): position a owns steps[offsets[a-begin] .. offsets[a-begin+1]),
  * strictly increasing in len and dist. Pointers are HOST pointers into pinned memory owned by the

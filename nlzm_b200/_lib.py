@@ -76,6 +76,6 @@ def load():
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(nvcc, sm_100a). There is no CPU fallback.")
         _lib = bind_prototypes(C.CDLL(LIB_PATH))
-        if _lib.nlzm_mf_abi_version() != 1:
+        if _lib.nlzm_mf_abi_version() != 2:
             raise RuntimeError("libnlzm_mf.so ABI version mismatch")
     return _lib

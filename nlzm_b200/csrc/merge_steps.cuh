@@ -8,7 +8,7 @@
 #pragma once
 #include "common.cuh"
 
-struct Step { u32 dist; u16 len; u16 pad; };      // mirrors nlzm_mf_step in include/nlzm_mf.h
+struct Step { u16 dist_lo, dist_hi, len; };        // mirrors nlzm_mf_step in include/nlzm_mf.h (6 bytes)
 
 struct FilterParams {
     const u64 *keys;      // sorted: (a_rel << 9) | len
@@ -38,7 +38,8 @@ NLZM_KERNEL_1D(step_filter, FilterParams)
 struct CompactParams { const u64 *keys; const u32 *dist; const u32 *keep; const u32 *out_idx; Step *steps; };
 DEV void step_compact_body(const CompactParams &p, u64 j) {
     if (!p.keep[j]) return;
-    Step s; s.dist = p.dist[j]; s.len = (u16)(p.keys[j] & 511u); s.pad = 0;
+    const u32 d = p.dist[j];
+    Step s; s.dist_lo = (u16)d; s.dist_hi = (u16)(d >> 16); s.len = (u16)(p.keys[j] & 511u);
     p.steps[p.out_idx[j]] = s;
 }
 NLZM_KERNEL_1D(step_compact, CompactParams)

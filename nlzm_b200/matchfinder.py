@@ -14,7 +14,8 @@ import numpy as np
 from . import _lib
 from ._lib import HT2, HT3, BT4, RK256, ALL  # noqa: F401
 
-STEP_DTYPE = np.dtype([("dist", "<u4"), ("len", "<u2"), ("reserved", "<u2")])
+RAW_STEP_DTYPE = np.dtype([("dist_lo", "<u2"), ("dist_hi", "<u2"), ("len", "<u2")])     # nlzm_mf_step, 6 bytes
+STEP_DTYPE = np.dtype([("dist", "<u4"), ("len", "<u2")])                                 # what the wrapper hands out
 
 
 class MatchFinderError(RuntimeError):
@@ -65,7 +66,8 @@ class MatchFinders:
 
     def FindAndUpdate(self, begin: int = 0, end: int | None = None, slot: int = 0, copy: bool = True):
         """Candidates of positions [begin, end) as (offsets u32[end-begin+1], steps STEP_DTYPE[n]).
-        Each step is one MatchTable::Update(dist, len) the reference finders would have issued."""
+        Each step is one MatchTable::Update(dist, len) the reference finders would have issued.
+        copy=False returns zero-copy views of the engine's pinned buffers instead (raw 6-byte records)."""
         end = self.file_len if end is None else end
         v = _lib.View()
         self._check(self._L.nlzm_mf_find(self._h, begin, end, slot, C.byref(v)), "find")
@@ -109,11 +111,13 @@ class MatchFinders:
         off = np.ctypeslib.as_array(C.cast(v.offsets, C.POINTER(C.c_uint32)), (n + 1,))
         m = int(v.n_steps)
         if m:
-            buf = (C.c_char * (m * STEP_DTYPE.itemsize)).from_address(v.steps)
-            steps = np.frombuffer(buf, dtype=STEP_DTYPE)
+            buf = (C.c_char * (m * RAW_STEP_DTYPE.itemsize)).from_address(v.steps)
+            raw = np.frombuffer(buf, dtype=RAW_STEP_DTYPE)
         else:
-            steps = np.zeros(0, dtype=STEP_DTYPE)
-        return (off.copy(), steps.copy()) if copy else (off, steps)
+            raw = np.zeros(0, dtype=RAW_STEP_DTYPE)
+        if not copy:
+            return off, raw                 # zero-copy view of the pinned buffers (fields dist_lo, dist_hi, len)
+        return off.copy(), unpack_steps(raw)
 
     def _check(self, rc, what):
         if rc:
@@ -131,6 +135,14 @@ class MatchFinders:
             self.Release()
         except Exception:
             pass
+
+
+def unpack_steps(raw: np.ndarray) -> np.ndarray:
+    """raw 6-byte records (copy=False views) -> STEP_DTYPE array with a 32-bit `dist` field"""
+    steps = np.empty(raw.size, dtype=STEP_DTYPE)
+    steps["dist"] = raw["dist_lo"].astype(np.uint32) | (raw["dist_hi"].astype(np.uint32) << 16)
+    steps["len"] = raw["len"]
+    return steps
 
 
 def profile(enable: bool, lib=None) -> None:

@@ -162,7 +162,7 @@ def test_properties_256mb_window(cuda_lib):
     """-window:28 needs >= 128 MiB of input (the reference shrinks the window to the file): 140 MB of
     long-range data in two blocks; every step must be a true in-window match, strictly increasing."""
     from nlzm_b200 import synth
-    from nlzm_b200.matchfinder import MatchFinders, geometry
+    from nlzm_b200.matchfinder import MatchFinders, geometry, unpack_steps
     x = synth.longrange(140_000_000, 77)
     assert geometry(x.size, 28, cuda_lib).hist_bits == 28
     with MatchFinders(cuda_lib) as mf:
@@ -170,6 +170,7 @@ def test_properties_256mb_window(cuda_lib):
         total = 0
         for i, (b, e) in enumerate([(0, 1 << 26), (1 << 26, x.size)]):
             off, st = mf.FindAndUpdate(b, e, slot=i, copy=False)
+            st = unpack_steps(st)
             _check_properties(x, off, st, b, 1 << 28)
             total += st.size
     assert total > x.size          # redundant data: several steps per position

@@ -4,7 +4,7 @@ import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nlzm_b200 import synth, sharding
-from nlzm_b200.matchfinder import MatchFinders
+from nlzm_b200.matchfinder import MatchFinders, unpack_steps
 
 kind, n, hb = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 block = int(sys.argv[4]) if len(sys.argv) > 4 else (1 << 28 if hb >= 27 else 1 << 27)   # big windows: big blocks (halo is re-merged per block)
@@ -14,7 +14,7 @@ with MatchFinders() as mf:
     mf.Init(hb, x, max_range=block)
     tot_ms = 0.0; tot_steps = 0
     for i, (b, e) in enumerate(sharding.split_blocks(0, n, block)):
-        t = time.time(); off, st = mf.FindAndUpdate(b, e, slot=i & 1, copy=False); wall = time.time() - t
+        t = time.time(); off, st = mf.FindAndUpdate(b, e, slot=i & 1, copy=False); wall = time.time() - t; st = unpack_steps(st)
         s = mf.stats(); tot_ms += s.ms_total; tot_steps += st.size
         dist, ln = st["dist"].astype(np.int64), st["len"].astype(np.int64)
         pos = np.repeat(np.arange(b, e, dtype=np.int64), np.diff(off.astype(np.int64)))
