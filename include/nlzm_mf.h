@@ -61,7 +61,7 @@ typedef struct {
     uint64_t file_len;         /* total input length in bytes (< 2^31) */
     int32_t device;            /* CUDA device ordinal */
     uint32_t finder_mask;      /* nlzm_mf_finder bits; 0 = all */
-    uint64_t max_range;        /* largest end-begin a find call will use; 0 = file_len */
+    uint64_t max_range;        /* largest end-begin a find call will use (<= 2^28); 0 = file_len */
 } nlzm_mf_config;
 
 /* The geometry the reference derives from (file_len, hist_bits); part of the matcher semantics. */
@@ -114,7 +114,8 @@ int nlzm_mf_fetch(nlzm_mf *mf, int slot, nlzm_mf_view *out);                    
 int nlzm_mf_get_stats(const nlzm_mf *mf, nlzm_mf_stats *out);
 
 /* Tuning / test knobs (no reference counterpart; results never depend on them):
- *   "ht_margin"      positions before a range for which the HT stage materialises per-position data (default 4 Mi)
+ *   "ht_margin"      positions before a range for which the HT stage materialises per-position data
+ *                    (default: the whole prefix, 12 bytes per position)
  *   "ht_coarse_log"  log2 of the coarse table spacing of the far prefix (default 20) */
 int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value);
 
