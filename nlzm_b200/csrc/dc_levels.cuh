@@ -361,7 +361,10 @@ DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         p.ptr[t0 + i] = pe;
     }
 }
-NLZM_KERNEL_CTA(dc_base, DcParams, NLZM_BASE_THREADS)
+#ifndef NLZM_BASE_MINBLOCKS
+#define NLZM_BASE_MINBLOCKS 1
+#endif
+NLZM_KERNEL_CTA_OCC(dc_base, DcParams, NLZM_BASE_THREADS, NLZM_BASE_MINBLOCKS)
 
 // ================================================================================================
 // merge levels
@@ -572,7 +575,10 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         for (u32 i = tid; i < nl; i += NLZM_MT_THREADS) p.corank[s.base + l0 + i] = r0 + ((u32)pos_l[i] - i);
     }
 }
-NLZM_KERNEL_CTA(dc_merge_tile, DcParams, NLZM_MT_THREADS)
+#ifndef NLZM_MT_MINBLOCKS
+#define NLZM_MT_MINBLOCKS 5
+#endif
+NLZM_KERNEL_CTA_OCC(dc_merge_tile, DcParams, NLZM_MT_THREADS, NLZM_MT_MINBLOCKS)
 
 // Left-half elements adopt their rank-nearest right-half neighbours as pg / ng when those are nearer
 // in rank than the pointers they already hold (every right-half position is greater). Separate launch:

@@ -32,8 +32,9 @@ typedef int64_t i64;
         nlzm_launch_end(st);                                                            \
     }
 // One CTA of NT threads runs name##_cta(p, block, thread, smem); dynamic shared memory.
-#define NLZM_KERNEL_CTA(name, ParamsT, NT)                                              \
-    __global__ void __launch_bounds__(NT) k_##name(const ParamsT p) {                   \
+#define NLZM_KERNEL_CTA(name, ParamsT, NT) NLZM_KERNEL_CTA_OCC(name, ParamsT, NT, 1)
+#define NLZM_KERNEL_CTA_OCC(name, ParamsT, NT, MINB)                                    \
+    __global__ void __launch_bounds__(NT, MINB) k_##name(const ParamsT p) {             \
         extern __shared__ __align__(16) u8 nlzm_smem[];                                 \
         name##_cta(p, blockIdx.x, threadIdx.x, nlzm_smem);                              \
     }                                                                                   \
@@ -89,6 +90,7 @@ typedef int cudaError_t;
 struct EmuCta { std::barrier<> *bar; };
 extern thread_local EmuCta nlzm_emu_cta;
 #define NLZM_CTA_SYNC() nlzm_emu_cta.bar->arrive_and_wait()
+#define NLZM_KERNEL_CTA_OCC(name, ParamsT, NT, MINB) NLZM_KERNEL_CTA(name, ParamsT, NT)
 #define NLZM_KERNEL_CTA(name, ParamsT, NT)                                              \
     static inline int launch_##name(const ParamsT &p, u64 grid, size_t smem, cudaStream_t st) { \
         if (grid == 0) return 0;                                                        \
