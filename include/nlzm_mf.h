@@ -115,7 +115,7 @@ int nlzm_mf_get_stats(const nlzm_mf *mf, nlzm_mf_stats *out);
 
 /* Tuning / test knobs (no reference counterpart; results never depend on them):
  *   "ht_margin"      positions before a range for which the HT stage materialises per-position data
- *                    (default: the whole prefix, 12 bytes per position)
+ *                    (default: the whole prefix, 12 bytes per position; smaller = less memory, slower look-ups)
  *   "ht_coarse_log"  log2 of the coarse table spacing of the far prefix (default 20) */
 int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value);
 

@@ -116,7 +116,7 @@ struct nlzm_mf {
     DevBuf k64[2], v32[2], rank, ptr, aux0, aux1, el[2], part;     // stages S/T
     DevBuf tk[2], tv[2], tcount, keep, out_idx;                    // tuples / merge
     DevBuf e_k[2], e_v[2], e_inv;                                  // BT short-length bucket sort (small windows)
-    DevBuf ht_tab, ht_gmax, ht_coarse, ht_cfirst, ht_clast, ht_ps, ht_pl, ht_pr;                 // HT: per-tile last-access tables, PS/PL/PR
+    DevBuf ht_tab, ht_gmax, ht_coarse, ht_cfirst, ht_clast, ht_ccount, ht_ps, ht_pl, ht_pr;                 // HT: per-tile last-access tables, PS/PL/PR
     DevBuf hblk, sl_k[2], sl_v[2], sl_cnt, sl_off;                 // RK table
     DevBuf hit_k[2], hit_v[2], hit_len, iv, val_k, val_v;          // RK hits / carry intervals
     DevBuf scalars;                                                // misc device scalars
@@ -347,6 +347,7 @@ int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     const u64 n_tiles = (n_acc - pos0 + NLZM_HT_TILE - 1) / NLZM_HT_TILE;
     CKI(ensure(ht_coarse, (n_coarse + 1) * nc * 4));
     CKI(ensure(ht_cfirst, (n_coarse + 1) * nc * 4)); CKI(ensure(ht_clast, (n_coarse + 1) * nc * 4));
+    CKI(ensure(ht_ccount, (n_coarse + 1) * nc * 4));
     CKI(ensure(ht_tab, n_tiles * nc * 4));
     CKI(ensure(ht_ps, (n_acc - pos0) * 4));
     if (c.rows == 2) { CKI(ensure(ht_pl, (n_acc - pos0) * 4)); CKI(ensure(ht_pr, (n_acc - pos0) * 4)); }
@@ -355,7 +356,7 @@ int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     const u64 n_groups_max = (max_tiles + NLZM_HT_GROUP - 1) / NLZM_HT_GROUP;
     CKI(ensure(ht_gmax, n_groups_max * nc * 4));
     HtTableParams tp;
-    tp.first_rows = nullptr; tp.last_rows = nullptr;
+    tp.first_rows = nullptr; tp.last_rows = nullptr; tp.count_rows = nullptr;
     tp.x = x.as<u8>(); tp.c = c; tp.x_limit = g.flen + NLZM_X_PAD;
     tp.ps = ht_ps.as<u32>(); tp.pl = ht_pl.as<u32>(); tp.pr = ht_pr.as<u32>();
     HtScanParams sp;
@@ -363,8 +364,8 @@ int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     if (n_coarse) {
         tp.pos0 = 0; tp.n_acc = pos0; tp.tile_log = ht_coarse_log; tp.n_tiles = (u32)n_coarse;
         tp.tile_last = ht_coarse.as<u32>();
-        tp.first_rows = ht_cfirst.as<u32>(); tp.last_rows = ht_clast.as<u32>();
-        CKI(launch_ht_tile_last(tp, n_coarse, nc * 8, st));
+        tp.first_rows = ht_cfirst.as<u32>(); tp.last_rows = ht_clast.as<u32>(); tp.count_rows = ht_ccount.as<u32>();
+        CKI(launch_ht_tile_last(tp, n_coarse, nc * 12, st));
         sp.tile_last = ht_coarse.as<u32>(); sp.init = nullptr; sp.final_row = base_row;
         sp.n_tiles = (u32)n_coarse; sp.n_groups = (u32)((n_coarse + NLZM_HT_GROUP - 1) / NLZM_HT_GROUP);
         launch_ht_tile_scan(sp, st);
@@ -377,7 +378,7 @@ int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     sp.n_tiles = (u32)n_tiles; sp.n_groups = (u32)((n_tiles + NLZM_HT_GROUP - 1) / NLZM_HT_GROUP);
     launch_ht_tile_scan(sp, st);
     CKI(launch_ht_prev(tp, n_tiles, nc * 2 + NLZM_HT_STAGE + 16, st));
-    HtFindParams fp{x.as<u8>(), g, c, ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>(), pos0, ht_coarse.as<u32>(), ht_cfirst.as<u32>(), ht_clast.as<u32>(), ht_coarse_log, own_b,
+    HtFindParams fp{x.as<u8>(), g, c, ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>(), pos0, ht_coarse.as<u32>(), ht_cfirst.as<u32>(), ht_clast.as<u32>(), ht_ccount.as<u32>(), ht_coarse_log, own_b,
                     (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
     launch_ht_find(fp, n_acc - own_b, st);
     return 0;
@@ -650,7 +651,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
     }
     DevBuf *all[] = {&mf->x, &mf->k64[0], &mf->k64[1], &mf->v32[0], &mf->v32[1], &mf->rank, &mf->ptr, &mf->el[0], &mf->el[1], &mf->part, &mf->aux0,
                      &mf->aux1, &mf->tk[0], &mf->tk[1], &mf->tv[0], &mf->tv[1], &mf->tcount, &mf->keep, &mf->out_idx,
-                     &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->ht_tab, &mf->ht_gmax, &mf->ht_coarse, &mf->ht_cfirst, &mf->ht_clast, &mf->ht_ps, &mf->ht_pl, &mf->ht_pr, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
+                     &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->ht_tab, &mf->ht_gmax, &mf->ht_coarse, &mf->ht_cfirst, &mf->ht_clast, &mf->ht_ccount, &mf->ht_ps, &mf->ht_pl, &mf->ht_pr, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
                      &mf->sl_v[0], &mf->sl_v[1], &mf->sl_cnt, &mf->sl_off, &mf->hit_k[0], &mf->hit_k[1], &mf->hit_v[0],
                      &mf->hit_v[1], &mf->hit_len, &mf->iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf};
     for (DevBuf *b : all) mf->release(*b);

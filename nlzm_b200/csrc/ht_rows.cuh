@@ -18,11 +18,12 @@
 //                    pushed an older entry), then the reference's match / check-bit / window logic
 // MatchFinderHT::Shift as written only clears cell 0 at each ring shift (NLZM.cpp:940-957); tables
 // never age, so the last-access tables cover the whole prefix [0, end) — streaming work, no sort.
-// PS/PL/PR are materialised from `pos0` on: by default 0 (whole prefix, 12 B per position). With the
-// "ht_margin" option they start that far before the answered range and the far prefix only gets one
-// coarse table per 2^ht_coarse_log positions; a chain step that lands there is resolved exactly from
-// the coarse tables, scanning text only when it falls between two accesses of one coarse tile
-// (measured on a late shard of 800 MB text: the scans cost far more than the 12 B per position save).
+// PS/PL/PR are materialised from `pos0` on: by default 0 (the whole prefix, 12 B per position). With the
+// "ht_margin" option they start that far before the answered range and the prefix before that only gets
+// coarse tables per 2^ht_coarse_log positions (table before the tile, first / last access and access
+// count inside it); a chain step that lands there is answered exactly from those, scanning text only when
+// the position lies between accesses of a bucket with three or more accesses in its tile. Measured on a
+// late shard of 800 MB text with an 8 Mi margin: those scans cost 70 ms, the whole-prefix walk 27 ms.
 #pragma once
 #include "common.cuh"
 #include "dc_levels.cuh"
@@ -38,8 +39,8 @@ struct HtCfg {
 #define NLZM_HT_TILE (1u << NLZM_HT_TILE_LOG)
 #define NLZM_HT_COARSE_LOG 20u                 // coarse tiles of the far prefix
 #define NLZM_HT_MARGIN 0xFFFFFFFFFFFFull        // PS/PL/PR start this far before the answered range: by default the
-                                               // whole prefix (12 B per position); a smaller margin (option "ht_margin")
-                                               // trades memory for slow exact look-ups in the far prefix
+                                               // whole prefix (12 B per position, streaming to build); a smaller margin
+                                               // (option "ht_margin") saves that memory but pays for it in look-ups
 #define NLZM_HT_THREADS 256
 #define NLZM_HT_STAGE 2048u                     // text bytes staged in shared memory by k_ht_prev
 
@@ -59,6 +60,7 @@ struct HtTableParams {
     u32 *tile_last;   // [n_tiles][1 << bits]: last access (+1) per bucket inside the tile, then: before the tile
     u32 *first_rows;  // out (coarse launch only, else null): [n_tiles][1 << bits] first access (+1) inside the tile
     u32 *last_rows;   // out (coarse launch only): copy of the per-tile last access before the scan overwrites it
+    u32 *count_rows;  // out (coarse launch only): accesses per bucket inside the tile
     u32 *ps, *pl, *pr;// per position - pos0: last access (+1, 0 = none) before it in bucket b, b-1, b+1
 };
 
@@ -66,15 +68,15 @@ struct HtTableParams {
 DEV void ht_tile_last_cta(const HtTableParams &p, u32 bid, u32 tid, u8 *smem) {
     u32 *tab = (u32 *)smem;
     const u32 nc = 1u << p.c.bits;
-    u32 *tmin = tab + nc;                                        // only with first_rows (launcher sizes the memory)
-    for (u32 i = tid; i < nc; i += NLZM_HT_THREADS) { tab[i] = 0; if (p.first_rows) tmin[i] = 0xFFFFFFFFu; }
+    u32 *tmin = tab + nc, *tcnt = tab + 2 * nc;                  // only with first_rows (launcher sizes the memory)
+    for (u32 i = tid; i < nc; i += NLZM_HT_THREADS) { tab[i] = 0; if (p.first_rows) { tmin[i] = 0xFFFFFFFFu; tcnt[i] = 0; } }
     NLZM_CTA_SYNC();
     const u64 t0 = p.pos0 + ((u64)bid << p.tile_log);
     const u64 t1 = t0 + (1ull << p.tile_log) < p.n_acc ? t0 + (1ull << p.tile_log) : p.n_acc;
     for (u64 a = t0 + tid; a < t1; a += NLZM_HT_THREADS) {
         const u32 b = ht_hash(p.x, a, p.c.nbytes) >> (32 - p.c.bits);
         nlzm_atomic_max(tab + b, (u32)a + 1u);
-        if (p.first_rows) nlzm_atomic_min(tmin + b, (u32)a + 1u);
+        if (p.first_rows) { nlzm_atomic_min(tmin + b, (u32)a + 1u); nlzm_atomic_add(tcnt + b, 1u); }
     }
     NLZM_CTA_SYNC();
     u32 *out = p.tile_last + (u64)bid * nc;
@@ -83,6 +85,7 @@ DEV void ht_tile_last_cta(const HtTableParams &p, u32 bid, u32 tid, u8 *smem) {
         if (p.first_rows) {
             p.last_rows[(u64)bid * nc + i] = tab[i];
             p.first_rows[(u64)bid * nc + i] = tmin[i] == 0xFFFFFFFFu ? 0u : tmin[i];
+            p.count_rows[(u64)bid * nc + i] = tcnt[i];
         }
     }
 }
@@ -261,6 +264,7 @@ struct HtFindParams {
     const u32 *coarse;         // [pos0 >> coarse_log][1 << bits]: table before each coarse tile of the far prefix
     const u32 *coarse_first;   // same shape: first access (+1) inside the coarse tile, 0 = none
     const u32 *coarse_last;    // same shape: last access (+1) inside the coarse tile, 0 = none
+    const u32 *coarse_count;   // same shape: number of accesses inside the coarse tile
     u32 coarse_log;
     u64 own_b;
     u32 bt_on;           // exhaustive BT4 runs too: it reports a candidate at least as near and as long for every
@@ -283,7 +287,8 @@ DEV u32 ht_last_before(const HtFindParams &p, u32 bucket, u64 q) {
     if (first == 0 || (u64)first - 1 >= q) return p.coarse[cell];      // no access of this bucket in [t0, q)
     const u32 last = p.coarse_last[cell];
     if ((u64)last - 1 < q) return last;                                 // the tile's last access lies before q
-    const u32 shift = 32 - p.c.bits;                                    // q sits between accesses of its tile: scan back
+    if (p.coarse_count[cell] == 2) return first;                        // first < q <= last and nothing in between
+    const u32 shift = 32 - p.c.bits;                                    // three or more accesses around q: scan back
     for (u64 a = q; a-- > t0; )
         if ((ht_hash(p.x, a, p.c.nbytes) >> shift) == bucket) return (u32)a + 1u;
     return p.coarse[cell];
