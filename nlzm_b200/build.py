@@ -1,4 +1,5 @@
-"""Builds the CUDA library in-tree: nlzm_b200/csrc/libnlzm_mf.so (sm_100a only)."""
+"""Builds the libraries in-tree: nlzm_b200/csrc/libnlzm_mf.so (CUDA engine, sm_100a only) and
+nlzm_b200/csrc/libnlzm_codec.so (C++ host pipeline on top of it)."""
 from __future__ import annotations
 
 import glob
@@ -30,3 +31,20 @@ def build_cuda(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, os.path.join(CSRC, "engine.cu")]
     subprocess.check_call(cmd, cwd=CSRC)
     return OUT
+
+
+CODEC_OUT = os.path.join(CSRC, "libnlzm_codec.so")
+
+
+def build_codec(force: bool = False) -> str:
+    """Host pipeline (parser + stream writer / reader); links the engine library next to it."""
+    build_cuda()
+    srcs = glob.glob(os.path.join(CSRC, "host", "*")) + glob.glob(os.path.join(HERE, "..", "include", "*"))
+    if not force and os.path.exists(CODEC_OUT) and \
+            all(os.path.getmtime(s) <= os.path.getmtime(CODEC_OUT) for s in srcs + [OUT]):
+        return CODEC_OUT
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cmd = [cxx, "-O2", "-g", "-std=c++17", "-Wall", "-fPIC", "-shared", os.path.join(CSRC, "host", "codec.cpp"),
+           "-o", CODEC_OUT, "-L" + CSRC, "-lnlzm_mf", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return CODEC_OUT

@@ -1,0 +1,316 @@
+// codec.cpp — libnlzm_codec: the host pipeline around the B200 match-finding engine.
+//
+// SURVEY.md §8 f1 (parser consumer + pipeline), f2 (stream writer), f4 (stream reader). C ABI in
+// include/nlzm_codec.h. Restates the reference's encode_file / decode_file drivers
+// (NLZM.cpp:1711-1910, 1912-2039) for a flat input: the whole file goes to HBM once
+// (GpuMatchFinders::Init), candidate blocks come back double-buffered (the GPU computes block N+1
+// while this thread parses and codes block N), and per chunk of `chunk_size` bytes one frame is
+// written. Ring shifts survive only as the coordinate offset the recent-distance reach test needs.
+//
+// The matcher stage has no CPU implementation here: without a CUDA device nlzm_codec_compress
+// fails with NLZM_CODEC_E_ENGINE.
+#include "../../../include/nlzm_codec.h"
+#include "../../../include/nlzm_mf_shim.hpp"
+#include "frame_coder.hpp"
+#include "parser.hpp"
+#include "stream_model.hpp"
+
+#include <chrono>
+#include <new>
+#include <stdlib.h>
+#include <string>
+
+using namespace nlzm_host;
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int rc, const std::string &why) {
+    g_error = why;
+    return rc;
+}
+
+double ms_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// GpuMatchFinders with the time spent blocked on a block hand-over accounted for. Unlike the shim's
+// own error path (the reference's ASSERT -> exit) a failing engine call is reported to the caller.
+struct TimedFinders {
+    GpuMatchFinders gpu;
+    double ms_wait = 0;
+    template <class T> void FindAndUpdate(T &st, uint64_t abs_pos) {
+        if (abs_pos >= gpu.cur_end) {
+            auto t0 = std::chrono::steady_clock::now();
+            gpu.FindAndUpdate(st, abs_pos);
+            ms_wait += ms_since(t0);
+        } else {
+            gpu.FindAndUpdate(st, abs_pos);
+        }
+    }
+};
+
+void write_length(FrameWriter &w, StreamModel &m, uint32_t excess) {
+    int head = excess < 7 ? (int)excess : 7;
+    w.put(m.len_head, head);
+    m.len_head.adapt(head);
+    if (excess >= 7) {
+        int hi = (int)((excess - 7) >> 4), lo = (int)((excess - 7) & 15);
+        w.put(m.len_tail_hi, hi);
+        w.put(m.len_tail_lo[hi], lo);
+        m.len_tail_hi.adapt(hi);
+        m.len_tail_lo[hi].adapt(lo);
+    }
+}
+
+void write_command(FrameWriter &w, StreamModel &m, const ParsedCommand &c, uint8_t literal) {
+    w.put(m.command, c.kind);
+    m.command.adapt(c.kind);
+    if (c.kind == kLiteral) {
+        int hi = literal >> 4, lo = literal & 15;
+        w.put(m.lit_hi, hi);
+        w.put(m.lit_lo[hi], lo);
+        m.lit_hi.adapt(hi);
+        m.lit_lo[hi].adapt(lo);
+    } else if (c.kind == kMatch) {
+        const uint32_t dist = c.value, excess = c.len - shortest_len(dist), ctx = excess < 3 ? excess : 3;
+        write_length(w, m, excess);
+        const DistCode dc = split_distance(dist);
+        const int hi = (int)(dc.slot >> 3), lo = (int)(dc.slot & 7);
+        w.put(m.slot_hi[ctx], hi);
+        w.put(m.slot_lo[ctx][hi], lo);
+        m.slot_hi[ctx].adapt(hi);
+        m.slot_lo[ctx][hi].adapt(lo);
+        if (dc.raw_bits > 0) {
+            // up to 3 raw bits travel as one field; longer tails as (all but the low nibble), (low nibble)
+            if (dc.raw_bits < 4) {
+                w.put_raw(dc.raw, dc.raw_bits);
+            } else {
+                if (dc.raw_bits > 4) w.put_raw(dc.raw >> 4, dc.raw_bits - 4);
+                w.put_raw(dc.raw & 15, 4);
+            }
+        }
+        m.recent.remember(dist);
+    } else {
+        const uint32_t dist = m.recent.d[c.value];
+        write_length(w, m, c.len - shortest_len(dist));
+        w.put_raw(c.value, 2);
+        m.recent.remember(dist);
+    }
+}
+
+uint32_t read_length_excess(FrameReader &r, StreamModel &m) {
+    uint32_t excess = (uint32_t)r.get(m.len_head);
+    m.len_head.adapt((int)excess);
+    if (excess == 7) {
+        int hi = r.get(m.len_tail_hi), lo = r.get(m.len_tail_lo[hi]);
+        m.len_tail_hi.adapt(hi);
+        m.len_tail_lo[hi].adapt(lo);
+        excess += ((uint32_t)hi << 4) + (uint32_t)lo;
+    }
+    return excess;
+}
+
+int hand_over(std::vector<uint8_t> &v, uint8_t **out, uint64_t *out_len) {
+    uint8_t *p = (uint8_t *)malloc(v.size() ? v.size() : 1);
+    if (!p) return fail(NLZM_CODEC_E_NOMEM, "out of host memory");
+    if (!v.empty()) memcpy(p, v.data(), v.size());
+    *out = p;
+    *out_len = v.size();
+    return 0;
+}
+
+int compress_impl(const uint8_t *in, uint64_t n, const nlzm_codec_config &cfg, std::vector<uint8_t> &out,
+                  nlzm_codec_stats &st) {
+    auto t0 = std::chrono::steady_clock::now();
+    const uint32_t window_bits = cfg.window_bits < 15 ? 15 : (cfg.window_bits > 28 ? 28 : cfg.window_bits);
+    nlzm_mf_geometry g;
+    if (nlzm_mf_get_geometry(n, window_bits, &g)) return fail(NLZM_CODEC_E_ARG, "bad geometry");
+
+    out.clear();
+    out.reserve((size_t)(n / 2 + 64));
+    out.push_back((uint8_t)(g.hist_bits >> 8));
+    out.push_back((uint8_t)g.hist_bits);
+    out.push_back((uint8_t)(g.frame_bits >> 8));
+    out.push_back((uint8_t)g.frame_bits);
+
+    if (n > 0) {
+        // engine: the calls of GpuMatchFinders::Init, with start-up errors returned instead of exit(-1)
+        TimedFinders finders;
+        {
+            nlzm_mf_config mc{};
+            mc.struct_size = sizeof mc;
+            mc.hist_bits = window_bits;
+            mc.file_len = n;
+            mc.device = cfg.device;
+            mc.finder_mask = NLZM_MF_ALL;
+            uint64_t block = cfg.block_len ? cfg.block_len : (g.window > (32u << 20) ? g.window : (32u << 20));
+            if (block > (1ull << 28)) block = 1ull << 28;
+            mc.max_range = block;
+            GpuMatchFinders &gpu = finders.gpu;
+            int rc = nlzm_mf_create(&mc, &gpu.mf);
+            if (rc) return fail(NLZM_CODEC_E_ENGINE, std::string("engine create failed: ") + nlzm_mf_last_error(nullptr));
+            rc = nlzm_mf_set_input(gpu.mf, in, n);
+            if (rc) {
+                std::string why = std::string("engine set_input failed: ") + nlzm_mf_last_error(gpu.mf);
+                gpu.Release();
+                return fail(NLZM_CODEC_E_ENGINE, why);
+            }
+            gpu.flen = n;
+            gpu.block = block;
+            gpu.cur_slot = 1;
+            gpu.submit_next();
+        }
+
+        StreamModel model;
+        model.reset();
+        FrameWriter frame;
+        SegmentParser<TimedFinders> parser(in, finders);
+        std::vector<ParsedCommand> cmds;
+
+        for (uint64_t base = 0; base < n; base += g.chunk_size) {
+            const uint64_t coded_end = base + g.chunk_size < n ? base + g.chunk_size : n;
+            const uint64_t feed_end = base + g.feed_size < n ? base + g.feed_size : n;
+            // the reference's ring is rebased by one window at a chunk start once it holds two
+            const uint64_t windows = base >> g.hist_bits;
+            const uint64_t rebase = (windows > 1 ? windows - 1 : 0) << g.hist_bits;
+
+            frame.begin();
+            for (uint64_t p = base; p < coded_end;) {
+                cmds.clear();
+                parser.parse(model, p, p - rebase, (uint32_t)(coded_end - p), (uint32_t)(feed_end - p), cmds);
+                ++st.parses;
+                for (const ParsedCommand &c : cmds) {
+                    write_command(frame, model, c, in[p]);
+                    if (c.kind == kLiteral) { ++st.literals; ++p; }
+                    else { c.kind == kMatch ? ++st.matches : ++st.reps; p += c.len; }
+                }
+            }
+            frame.end(out);
+            ++st.frames;
+        }
+        st.steps_served = finders.gpu.steps_served;
+        st.engine_blocks = finders.gpu.blocks_fetched;
+        st.ms_engine_wait = finders.ms_wait;
+        finders.gpu.Release();
+    }
+    out.insert(out.end(), 4, 0);             // a frame with zero ops ends the stream
+    st.in_bytes = n;
+    st.out_bytes = out.size();
+    st.ms_total = ms_since(t0);
+    return 0;
+}
+
+int decompress_impl(const uint8_t *in, uint64_t n, std::vector<uint8_t> &out) {
+    if (n < 8) return fail(NLZM_CODEC_E_STREAM, "stream shorter than header + end marker");
+    const uint32_t hist_bits = ((uint32_t)in[0] << 8) | in[1], frame_bits = ((uint32_t)in[2] << 8) | in[3];
+    if (hist_bits < 10 || hist_bits > 28 || frame_bits < 12 || frame_bits > 20)
+        return fail(NLZM_CODEC_E_STREAM, "bad stream header");
+    StreamModel model;
+    model.reset();
+    FrameReader frame;
+    out.clear();
+    uint64_t at = 4;
+    for (;;) {
+        int64_t size = frame.begin(in + at, (size_t)(n - at));
+        if (size < 0) return fail(NLZM_CODEC_E_STREAM, "malformed frame header at offset " + std::to_string(at));
+        if (size == 0) break;
+        while (frame.ops_left() > 0) {
+            int kind = frame.get(model.command);
+            model.command.adapt(kind);
+            if (kind == kLiteral) {
+                int hi = frame.get(model.lit_hi), lo = frame.get(model.lit_lo[hi]);
+                model.lit_hi.adapt(hi);
+                model.lit_lo[hi].adapt(lo);
+                out.push_back((uint8_t)((hi << 4) | lo));
+            } else if (kind == kMatch || kind == kRepeat) {
+                uint32_t dist, len;
+                if (kind == kMatch) {
+                    const uint32_t excess = read_length_excess(frame, model), ctx = excess < 3 ? excess : 3;
+                    const int hi = frame.get(model.slot_hi[ctx]), lo = frame.get(model.slot_lo[ctx][hi]);
+                    model.slot_hi[ctx].adapt(hi);
+                    model.slot_lo[ctx][hi].adapt(lo);
+                    uint32_t v = ((uint32_t)hi << 3) | (uint32_t)lo;
+                    if (v >= 4) {
+                        const uint32_t raw_bits = (v >> 1) - 1;
+                        if (raw_bits > 26) return fail(NLZM_CODEC_E_STREAM, "distance slot out of range");
+                        uint32_t raw;
+                        if (raw_bits < 4) raw = frame.get_raw(raw_bits);
+                        else {
+                            raw = raw_bits > 4 ? frame.get_raw(raw_bits - 4) << 4 : 0;
+                            raw += frame.get_raw(4);
+                        }
+                        v = join_distance(v, raw_bits, raw);
+                    }
+                    dist = v + 1;
+                    len = excess + shortest_len(dist);
+                } else {
+                    dist = model.recent.d[frame.get_raw(2)];
+                    len = read_length_excess(frame, model) + shortest_len(dist);
+                }
+                model.recent.remember(dist);
+                if (frame.bad()) break;
+                if (dist > out.size()) return fail(NLZM_CODEC_E_STREAM, "distance reaches before the start of the output");
+                size_t from = out.size() - dist;
+                out.resize(out.size() + len);
+                uint8_t *o = out.data();
+                for (size_t i = 0, to = out.size() - len; i < len; i++) o[to + i] = o[from + i];
+            } else {
+                return fail(NLZM_CODEC_E_STREAM, "unknown command");
+            }
+            if (frame.bad()) break;
+        }
+        if (frame.bad()) return fail(NLZM_CODEC_E_STREAM, "frame at offset " + std::to_string(at) + " is truncated");
+        at += (uint64_t)size;
+        if (n - at < 4) return fail(NLZM_CODEC_E_STREAM, "missing end marker");
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nlzm_codec_abi_version(void) { return NLZM_CODEC_ABI_VERSION; }
+
+int nlzm_codec_compress(const uint8_t *in, uint64_t in_len, const nlzm_codec_config *cfg, uint8_t **out,
+                        uint64_t *out_len, nlzm_codec_stats *stats) {
+    if (!cfg || cfg->struct_size != sizeof(nlzm_codec_config) || !out || !out_len || (!in && in_len))
+        return fail(NLZM_CODEC_E_ARG, "bad argument");
+    if (in_len >= (1ull << 31)) return fail(NLZM_CODEC_E_ARG, "input must be smaller than 2^31 bytes");
+    *out = nullptr;
+    *out_len = 0;
+    nlzm_codec_stats st{};
+    try {
+        std::vector<uint8_t> v;
+        int rc = compress_impl(in, in_len, *cfg, v, st);
+        if (rc) return rc;
+        rc = hand_over(v, out, out_len);
+        if (rc) return rc;
+    } catch (const std::bad_alloc &) {
+        return fail(NLZM_CODEC_E_NOMEM, "out of host memory");
+    }
+    if (stats) *stats = st;
+    return 0;
+}
+
+int nlzm_codec_decompress(const uint8_t *in, uint64_t in_len, uint8_t **out, uint64_t *out_len) {
+    if (!in || !out || !out_len) return fail(NLZM_CODEC_E_ARG, "bad argument");
+    *out = nullptr;
+    *out_len = 0;
+    try {
+        std::vector<uint8_t> v;
+        int rc = decompress_impl(in, in_len, v);
+        if (rc) return rc;
+        return hand_over(v, out, out_len);
+    } catch (const std::bad_alloc &) {
+        return fail(NLZM_CODEC_E_NOMEM, "out of host memory");
+    }
+}
+
+void nlzm_codec_free(uint8_t *p) { free(p); }
+
+const char *nlzm_codec_last_error(void) { return g_error.c_str(); }
+
+}  // extern "C"
