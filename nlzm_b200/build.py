@@ -44,7 +44,7 @@ def build_codec(force: bool = False) -> str:
             all(os.path.getmtime(s) <= os.path.getmtime(CODEC_OUT) for s in srcs + [OUT]):
         return CODEC_OUT
     cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
-    cmd = [cxx, "-O2", "-g", "-std=c++17", "-Wall", "-fPIC", "-shared", os.path.join(CSRC, "host", "codec.cpp"),
+    cmd = [cxx, "-O3", "-g", "-std=c++17", "-Wall", "-fPIC", "-shared", os.path.join(CSRC, "host", "codec.cpp"),
            "-o", CODEC_OUT, "-L" + CSRC, "-lnlzm_mf", "-Wl,-rpath,$ORIGIN"]
     subprocess.check_call(cmd, cwd=CSRC)
     return CODEC_OUT

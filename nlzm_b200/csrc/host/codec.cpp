@@ -13,6 +13,7 @@
 #include "../../../include/nlzm_mf_shim.hpp"
 #include "frame_coder.hpp"
 #include "parser.hpp"
+#include "pipeline.hpp"
 #include "stream_model.hpp"
 
 #include <chrono>
@@ -35,70 +36,25 @@ double ms_since(std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
-// GpuMatchFinders with the time spent blocked on a block hand-over accounted for. Unlike the shim's
-// own error path (the reference's ASSERT -> exit) a failing engine call is reported to the caller.
+// GpuMatchFinders (double-buffered candidate blocks) read directly: a position's steps are folded
+// into the staircase in one pass (Staircase::merge_steps) instead of one Update call per step, and
+// the time spent blocked on a block hand-over is accounted for.
 struct TimedFinders {
     GpuMatchFinders gpu;
     double ms_wait = 0;
     template <class T> void FindAndUpdate(T &st, uint64_t abs_pos) {
         if (abs_pos >= gpu.cur_end) {
             auto t0 = std::chrono::steady_clock::now();
-            gpu.FindAndUpdate(st, abs_pos);
+            while (abs_pos >= gpu.cur_end) gpu.advance();
             ms_wait += ms_since(t0);
-        } else {
-            gpu.FindAndUpdate(st, abs_pos);
         }
+        const uint64_t i = abs_pos - gpu.cur_begin;
+        const nlzm_mf_step *s = gpu.view.steps + gpu.view.offsets[i];
+        const uint32_t n = gpu.view.offsets[i + 1] - gpu.view.offsets[i];
+        st.merge_steps(n, [s](uint32_t j) { return NLZM_MF_STEP_DIST(s[j]); }, [s](uint32_t j) { return (uint32_t)s[j].len; });
+        gpu.steps_served += n;
     }
 };
-
-void write_length(FrameWriter &w, StreamModel &m, uint32_t excess) {
-    int head = excess < 7 ? (int)excess : 7;
-    w.put(m.len_head, head);
-    m.len_head.adapt(head);
-    if (excess >= 7) {
-        int hi = (int)((excess - 7) >> 4), lo = (int)((excess - 7) & 15);
-        w.put(m.len_tail_hi, hi);
-        w.put(m.len_tail_lo[hi], lo);
-        m.len_tail_hi.adapt(hi);
-        m.len_tail_lo[hi].adapt(lo);
-    }
-}
-
-void write_command(FrameWriter &w, StreamModel &m, const ParsedCommand &c, uint8_t literal) {
-    w.put(m.command, c.kind);
-    m.command.adapt(c.kind);
-    if (c.kind == kLiteral) {
-        int hi = literal >> 4, lo = literal & 15;
-        w.put(m.lit_hi, hi);
-        w.put(m.lit_lo[hi], lo);
-        m.lit_hi.adapt(hi);
-        m.lit_lo[hi].adapt(lo);
-    } else if (c.kind == kMatch) {
-        const uint32_t dist = c.value, excess = c.len - shortest_len(dist), ctx = excess < 3 ? excess : 3;
-        write_length(w, m, excess);
-        const DistCode dc = split_distance(dist);
-        const int hi = (int)(dc.slot >> 3), lo = (int)(dc.slot & 7);
-        w.put(m.slot_hi[ctx], hi);
-        w.put(m.slot_lo[ctx][hi], lo);
-        m.slot_hi[ctx].adapt(hi);
-        m.slot_lo[ctx][hi].adapt(lo);
-        if (dc.raw_bits > 0) {
-            // up to 3 raw bits travel as one field; longer tails as (all but the low nibble), (low nibble)
-            if (dc.raw_bits < 4) {
-                w.put_raw(dc.raw, dc.raw_bits);
-            } else {
-                if (dc.raw_bits > 4) w.put_raw(dc.raw >> 4, dc.raw_bits - 4);
-                w.put_raw(dc.raw & 15, 4);
-            }
-        }
-        m.recent.remember(dist);
-    } else {
-        const uint32_t dist = m.recent.d[c.value];
-        write_length(w, m, c.len - shortest_len(dist));
-        w.put_raw(c.value, 2);
-        m.recent.remember(dist);
-    }
-}
 
 uint32_t read_length_excess(FrameReader &r, StreamModel &m) {
     uint32_t excess = (uint32_t)r.get(m.len_head);
@@ -163,33 +119,10 @@ int compress_impl(const uint8_t *in, uint64_t n, const nlzm_codec_config &cfg, s
             gpu.submit_next();
         }
 
-        StreamModel model;
-        model.reset();
-        FrameWriter frame;
-        SegmentParser<TimedFinders> parser(in, finders);
-        std::vector<ParsedCommand> cmds;
-
-        for (uint64_t base = 0; base < n; base += g.chunk_size) {
-            const uint64_t coded_end = base + g.chunk_size < n ? base + g.chunk_size : n;
-            const uint64_t feed_end = base + g.feed_size < n ? base + g.feed_size : n;
-            // the reference's ring is rebased by one window at a chunk start once it holds two
-            const uint64_t windows = base >> g.hist_bits;
-            const uint64_t rebase = (windows > 1 ? windows - 1 : 0) << g.hist_bits;
-
-            frame.begin();
-            for (uint64_t p = base; p < coded_end;) {
-                cmds.clear();
-                parser.parse(model, p, p - rebase, (uint32_t)(coded_end - p), (uint32_t)(feed_end - p), cmds);
-                ++st.parses;
-                for (const ParsedCommand &c : cmds) {
-                    write_command(frame, model, c, in[p]);
-                    if (c.kind == kLiteral) { ++st.literals; ++p; }
-                    else { c.kind == kMatch ? ++st.matches : ++st.reps; p += c.len; }
-                }
-            }
-            frame.end(out);
-            ++st.frames;
-        }
+        EncodeCounters ec;
+        encode_stream(in, n, g.hist_bits, g.chunk_size, g.feed_size, finders, out, ec);
+        st.literals = ec.literals; st.matches = ec.matches; st.reps = ec.reps;
+        st.frames = ec.frames; st.parses = ec.parses;
         st.steps_served = finders.gpu.steps_served;
         st.engine_blocks = finders.gpu.blocks_fetched;
         st.ms_engine_wait = finders.ms_wait;

@@ -48,6 +48,23 @@ class Staircase {
         for (uint32_t i = known + 1; i <= len; i++) d[i] = dist;
         if (len > top) top = len;
     }
+    // A whole position's steps in one pass: the same result as Update(dist_j, len_j) for j = 0..n-1
+    // when the steps are strictly increasing in len and dist (the engine's contract, nlzm_mf.h) —
+    // step j then only matters for lengths above len_{j-1}, so the work is O(longest) instead of
+    // O(sum of lengths).
+    template <class DistOf, class LenOf> void merge_steps(uint32_t n, DistOf dist_of, LenOf len_of) {
+        if (n == 0) return;
+        uint32_t *d = &buf_[at_];
+        uint32_t i = 0, len = 0;
+        for (uint32_t j = 0; j < n; j++) {
+            const uint32_t dist = dist_of(j);
+            len = len_of(j);
+            const uint32_t known = top < len ? top : len;
+            for (; i <= known; i++) d[i] = dist < d[i] ? dist : d[i];
+            for (; i <= len; i++) d[i] = dist;
+        }
+        if (len > top) top = len;
+    }
     // one position forward (MatchTable::CarryFrom with shift 1, NLZM.cpp:836-846)
     void advance() {
         if (top <= 1) { top = 0; return; }
@@ -93,12 +110,15 @@ template <class Finders> class SegmentParser {
         node_[1] = {kUnreached, 0, 0, 0, kLiteral};
         recent_[1] = recent_[0];
 
+        ++stamp_;                                     // prices are fixed for the segment: memoise them
+        const uint32_t match_cmd = m.command.price(kMatch), repeat_cmd = m.command.price(kRepeat) + (2u << kPriceShift);
+
         uint32_t p = 0, end = 1;
         for (; p < end; ++p) {
             const Node from = node_[p];
             const RecentDistances &from_recent = recent_[p & kRingMask];
 
-            relax(p + 1, from.price + m.price_literal(here[p]), p, kLiteral, 0, 0, from_recent, 0);
+            relax(p + 1, from.price + literal_price(m, here[p]), p, kLiteral, 0, 0, from_recent, 0);
 
             st.advance();
             if (st.top > 0) {
@@ -119,27 +139,41 @@ template <class Finders> class SegmentParser {
 
             uint32_t met = 0;                         // recent distances seen among the candidates
             const uint32_t step = top >= kLenMin + 16 ? (top - kLenMin) >> 4 : 1;
+            uint32_t run_dist = 0, shortest = 0, slot = 0, raw_price = 0;     // per run of equal distances
+            int recent_index = -1;
             for (uint32_t len = top; len >= kLenMin; len = len > step ? len - step : 0) {
                 const uint32_t dist = st[len];
-                if (len < shortest_len(dist)) continue;
-                relax(p + len, from.price + m.price_match(dist, len), p, kMatch, len, dist, from_recent, dist);
-                int r = from_recent.index_of(dist);
-                if (r < 0) continue;
-                met |= 1u << r;
-                relax(p + len, from.price + m.price_repeat(dist, len), p, kRepeat, len, (uint32_t)r, from_recent, dist);
+                if (dist != run_dist) {
+                    run_dist = dist;
+                    shortest = shortest_len(dist);
+                    const DistCode dc = split_distance(dist);
+                    slot = dc.slot;
+                    raw_price = dc.raw_bits << kPriceShift;
+                    recent_index = from_recent.index_of(dist);
+                }
+                if (len < shortest) continue;
+                const uint32_t excess = len - shortest;
+                const uint32_t length_part = length_price(m, excess);
+                relax(p + len, from.price + match_cmd + length_part + raw_price + slot_price(m, excess < 3 ? excess : 3, slot),
+                      p, kMatch, len, dist, from_recent, dist);
+                if (recent_index < 0) continue;
+                met |= 1u << recent_index;
+                relax(p + len, from.price + repeat_cmd + length_part, p, kRepeat, len, (uint32_t)recent_index, from_recent, dist);
             }
-            if (met != 15) {
+            if (met != 15 && limit - p >= kLenMin) {
                 const uint64_t here_shifted = shifted_start + p;
+                const uint32_t cap = limit - p < kLenMax ? limit - p : kLenMax;     // longer is clamped anyway
+                const uint16_t head = load16(here + p);
                 for (int r = 0; r < 4; r++) {
                     const uint32_t dist = from_recent.d[r];
                     if ((met >> r & 1) || dist >= here_shifted) continue;
                     const uint8_t *src = here + p - dist;
-                    uint32_t cap = limit - p, len = 0;
-                    while (len < cap && src[len] == here[p + len]) ++len;
-                    if (len > kLenMax) len = kLenMax;
+                    if (load16(src) != head) continue;                  // every usable length is >= 2
+                    const uint32_t len = 2 + common_prefix(src + 2, here + p + 2, cap - 2);
                     if (len < shortest_len(dist)) continue;
                     while (end < len + p) node_[++end].price = kUnreached;
-                    relax(p + len, from.price + m.price_repeat(dist, len), p, kRepeat, len, (uint32_t)r, from_recent, dist);
+                    relax(p + len, from.price + repeat_cmd + length_price(m, len - shortest_len(dist)), p, kRepeat, len,
+                          (uint32_t)r, from_recent, dist);
                 }
             }
         }
@@ -173,10 +207,43 @@ template <class Finders> class SegmentParser {
         if (remember) r.remember(remember);
     }
 
+    static uint16_t load16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+    static uint32_t common_prefix(const uint8_t *a, const uint8_t *b, uint32_t cap) {
+        uint32_t n = 0;
+        while (n + 8 <= cap) {
+            uint64_t va, vb;
+            memcpy(&va, a + n, 8);
+            memcpy(&vb, b + n, 8);
+            if (va != vb) return n + (uint32_t)(__builtin_ctzll(va ^ vb) >> 3);
+            n += 8;
+        }
+        while (n < cap && a[n] == b[n]) ++n;
+        return n;
+    }
+    // memoised prices, valid while stamp matches the current segment
+    struct Memo { uint32_t stamp, price; };
+    uint32_t literal_price(const StreamModel &m, uint8_t y) {
+        Memo &c = lit_memo_[y];
+        if (c.stamp != stamp_) c = {stamp_, m.price_literal(y)};
+        return c.price;
+    }
+    uint32_t length_price(const StreamModel &m, uint32_t excess) {
+        Memo &c = len_memo_[excess];
+        if (c.stamp != stamp_) c = {stamp_, m.price_length(excess)};
+        return c.price;
+    }
+    uint32_t slot_price(const StreamModel &m, uint32_t ctx, uint32_t slot) {
+        Memo &c = slot_memo_[ctx][slot];
+        if (c.stamp != stamp_) c = {stamp_, m.slot_hi[ctx].price((int)(slot >> 3)) + m.slot_lo[ctx][slot >> 3].price((int)(slot & 7))};
+        return c.price;
+    }
+
     const uint8_t *x_;
     Finders &finders_;
     std::vector<Node> node_;
     RecentDistances recent_[kRingMask + 1];
+    uint32_t stamp_ = 0;
+    Memo lit_memo_[256] = {}, len_memo_[kLenMax + 1] = {}, slot_memo_[4][64] = {};
 };
 
 }  // namespace nlzm_host

@@ -69,13 +69,20 @@ template <int BITS> struct Table {
     uint32_t price(int y) const { return prices()(freq(y)); }
 
     // after coding y: boundaries at or below y drift towards their floor (their own index, which
-    // keeps every slice non-empty), boundaries above y towards a ceiling just past 2^14
-    void adapt(int y) {
-        constexpr int ceiling_bias = (int)kProbOne + (1 << kAdaptShift) - 1 - N;
-        for (int x = 1; x < N; x++) {
-            int target = x <= y ? x : ceiling_bias + x;
-            cum[x] = (uint16_t)(cum[x] + ((target - (int)cum[x]) >> kAdaptShift));
+    // keeps every slice non-empty), boundaries above y towards a ceiling just past 2^14. All values
+    // and differences fit in 16 signed bits, so the whole row updates in 16-bit lanes.
+    struct Targets {
+        int16_t row[N][N];
+        constexpr Targets() : row{} {
+            constexpr int ceiling_bias = (int)kProbOne + (1 << kAdaptShift) - 1 - N;
+            for (int y = 0; y < N; y++)
+                for (int x = 0; x < N; x++) row[y][x] = (int16_t)(x <= y ? x : ceiling_bias + x);
         }
+    };
+    static constexpr Targets kTargets{};
+    void adapt(int y) {
+        const int16_t *t = kTargets.row[y];
+        for (int x = 0; x < N; x++) cum[x] = (uint16_t)(cum[x] + ((int16_t)(t[x] - (int16_t)cum[x]) >> kAdaptShift));
     }
     // symbol whose slice holds f (decoder)
     int find(uint32_t f) const {
