@@ -102,6 +102,50 @@ def cpu_matcher_mbs(x_sample: np.ndarray, hist_bits: int):
     return x_sample.size / secs / 1e6, "port", secs
 
 
+COMPRESS_SAMPLE = 16 << 20
+
+
+def compress_ours(x: np.ndarray, hist_bits: int, device: int):
+    """End-to-end compress (BASELINE.json metric, second half) through this repo's own host pipeline
+    (libnlzm_codec: parser + model + rANS writer over the engine), host bytes in, stream bytes out."""
+    try:
+        from nlzm_b200 import codec
+        codec.compress(x[:1 << 20], hist_bits, device=device)          # warm-up
+        t = time.perf_counter()
+        blob, st = codec.compress(x, hist_bits, device=device, with_stats=True)
+        secs = time.perf_counter() - t
+        t = time.perf_counter()
+        ok = codec.decompress(blob) == x.tobytes()
+        dsecs = time.perf_counter() - t
+        return {"value": x.size / secs / 1e6, "unit": "MB/s", "ratio": len(blob) / x.size, "stream_bytes": len(blob),
+                "sample": f"first {x.size} bytes of the same text, -window:{hist_bits}", "roundtrip": bool(ok),
+                "decompress_MBps": x.size / dsecs / 1e6, "engine_wait_ms": st["ms_engine_wait"],
+                "path": "nlzm_codec_compress: engine blocks double-buffered against one host thread of parsing + rANS coding"}
+    except Exception as e:  # the headline matcher numbers must not depend on this leg
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
+def compress_reference(x: np.ndarray, hist_bits: int):
+    """The pristine reference CLI (oracle/_ref/nlzm_r0 -window:N c) on a bounded sample, one thread."""
+    try:
+        import tempfile
+        from oracle import refbind as rb
+        if not os.path.exists(rb.REF_R0):
+            return {"unavailable": "oracle/_ref/nlzm_r0 not built"}
+        with tempfile.TemporaryDirectory() as td:
+            src, dst = os.path.join(td, "in.bin"), os.path.join(td, "out.nlzm")
+            x.tofile(src)
+            t = time.perf_counter()
+            rb.r0_cli(f"-window:{hist_bits}", "c", src, dst)
+            secs = time.perf_counter() - t
+            size = os.path.getsize(dst)
+        return {"value": x.size / secs / 1e6, "unit": "MB/s", "ratio": size / x.size, "stream_bytes": size,
+                "sample": f"first {x.size} bytes of the same text, -window:{hist_bits}", "cores": 1,
+                "path": "nlzm_r0 c (unmodified reference, file in / file out)"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -123,7 +167,8 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "MB/s", "cores": 1, "kind": kind, "sample": sample,
                              "host_cores_available": os.cpu_count()},
             "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0,
+            "compress": compress_reference(x, HIST_BITS)}
     print(json.dumps(line), flush=True)
 
 
@@ -302,6 +347,8 @@ def run_ours(args):
                                            f"with the shipped 256-test cap + carry/skip rule, {cpu_secs:.1f} s",
                                  "host_cores_available": os.cpu_count()},
                 "clocks": clocks}
+        if world == 1:
+            line["compress"] = compress_ours(x_pin.numpy()[:COMPRESS_SAMPLE], args.hist_bits, local)
         print(json.dumps(line), flush=True)
     mf.Release()
     if world > 1:
