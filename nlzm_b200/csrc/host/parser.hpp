@@ -106,9 +106,7 @@ template <class Finders> class SegmentParser {
         Staircase &st = carried;
 
         node_[0] = {0, 0, 0, 0, kNone};
-        recent_[0] = m.recent;
         node_[1] = {kUnreached, 0, 0, 0, kLiteral};
-        recent_[1] = recent_[0];
 
         ++stamp_;                                     // prices are fixed for the segment: memoise them
         const uint32_t match_cmd = m.command.price(kMatch), repeat_cmd = m.command.price(kRepeat) + (2u << kPriceShift);
@@ -116,9 +114,18 @@ template <class Finders> class SegmentParser {
         uint32_t p = 0, end = 1;
         for (; p < end; ++p) {
             const Node from = node_[p];
-            const RecentDistances &from_recent = recent_[p & kRingMask];
+            // the recent distances on the best path to p: those of its predecessor, plus the distance
+            // of the match that leads here (repeats and literals change nothing). Derived when p is
+            // visited — its predecessor is final by then — rather than copied at every relaxation.
+            RecentDistances &from_recent = recent_[p & kRingMask];
+            if (p == 0) {
+                from_recent = m.recent;
+            } else {
+                from_recent = recent_[from.from & kRingMask];
+                if (from.kind == kMatch) from_recent.remember(from.value);
+            }
 
-            relax(p + 1, from.price + literal_price(m, here[p]), p, kLiteral, 0, 0, from_recent, 0);
+            relax(p + 1, from.price + literal_price(m, here[p]), p, kLiteral, 0, 0);
 
             st.advance();
             if (st.top > 0) {
@@ -155,10 +162,10 @@ template <class Finders> class SegmentParser {
                 const uint32_t excess = len - shortest;
                 const uint32_t length_part = length_price(m, excess);
                 relax(p + len, from.price + match_cmd + length_part + raw_price + slot_price(m, excess < 3 ? excess : 3, slot),
-                      p, kMatch, len, dist, from_recent, dist);
+                      p, kMatch, len, dist);
                 if (recent_index < 0) continue;
                 met |= 1u << recent_index;
-                relax(p + len, from.price + repeat_cmd + length_part, p, kRepeat, len, (uint32_t)recent_index, from_recent, dist);
+                relax(p + len, from.price + repeat_cmd + length_part, p, kRepeat, len, (uint32_t)recent_index);
             }
             if (met != 15 && limit - p >= kLenMin) {
                 const uint64_t here_shifted = shifted_start + p;
@@ -172,8 +179,7 @@ template <class Finders> class SegmentParser {
                     const uint32_t len = 2 + common_prefix(src + 2, here + p + 2, cap - 2);
                     if (len < shortest_len(dist)) continue;
                     while (end < len + p) node_[++end].price = kUnreached;
-                    relax(p + len, from.price + repeat_cmd + length_price(m, len - shortest_len(dist)), p, kRepeat, len,
-                          (uint32_t)r, from_recent, dist);
+                    relax(p + len, from.price + repeat_cmd + length_price(m, len - shortest_len(dist)), p, kRepeat, len, (uint32_t)r);
                 }
             }
         }
@@ -197,14 +203,9 @@ template <class Finders> class SegmentParser {
         uint32_t value;
         uint8_t kind;
     };
-    void relax(uint32_t to, uint32_t price, uint32_t from, uint8_t kind, uint32_t len, uint32_t value,
-               const RecentDistances &from_recent, uint32_t remember) {
+    void relax(uint32_t to, uint32_t price, uint32_t from, uint8_t kind, uint32_t len, uint32_t value) {
         Node &n = node_[to];
-        if (!(n.price > price)) return;
-        n = {price, (uint16_t)from, (uint16_t)len, value, kind};
-        RecentDistances &r = recent_[to & kRingMask];
-        r = from_recent;
-        if (remember) r.remember(remember);
+        if (n.price > price) n = {price, (uint16_t)from, (uint16_t)len, value, kind};
     }
 
     static uint16_t load16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
