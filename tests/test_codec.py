@@ -153,3 +153,26 @@ def test_compress_live_against_reference_parser_and_decoder_gpu(tmp_path, codec_
     open(ours, "wb").write(blob)
     rb.r0_cli("d", ours, back)
     assert open(back, "rb").read() == x.tobytes()
+
+
+@pytest.mark.parametrize("kind", ["ab", "abc_runs", "period", "zeros_ones", "words"])
+def test_compress_fuzz_against_reference_parser_emulated(tmp_path, codec_emu, kind):
+    """Small adversarial inputs (tiny alphabets, periods, runs, lengths around the 264-byte cap and the
+    4096-byte segment cap, several chunks): own parser + coder vs the reference's, same emulated engine."""
+    from oracle import refbind as rb
+    from nlzm_b200 import codec
+    from test_fuzz import _gen
+    for path in (rb.REF_EMU_SO, rb.REF_R0):
+        if not os.path.exists(path):
+            pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(sum(kind.encode()) + 1)
+    src, ref = str(tmp_path / "in.bin"), str(tmp_path / "ref.nlzm")
+    for n in (2, 3, 4, 7, 263, 264, 265, 266, 700, 4095, 4096, 4097, 4400, 14_848, 14_849, 31_000):
+        x = _gen(kind, n, rng)
+        x.tofile(src)
+        if os.path.exists(ref):
+            os.remove(ref)
+        rb.engine_fed_encode(src, ref, 15, emu=True, block_len=20_000)
+        blob = codec.compress(x, 15, block_len=9_000, lib=codec_emu)
+        assert blob == open(ref, "rb").read(), (kind, n)
+        assert codec.decompress(blob, lib=codec_emu) == x.tobytes(), (kind, n)
