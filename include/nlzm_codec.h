@@ -7,8 +7,8 @@
  *
  *   nlzm_codec_compress    <- encode_file(fin, fout, hist_bits)            NLZM.cpp:1711-1910
  *                             = parse_table (1464-1651) + model_encode_*  (1274-1367, 1428-1439)
- *                             + CodeFrame (560-640), with the four finder objects replaced by one
- *                             GpuMatchFinders (nlzm_mf_shim.hpp); the `-window:N` clamp of main()
+ *                             + CodeFrame (560-640), with the four finder objects replaced by the
+ *                             engine (nlzm_mf.h, double-buffered blocks); the `-window:N` clamp of main()
  *                             (NLZM.cpp:2085) is applied to window_bits
  *   nlzm_codec_decompress  <- decode_file(fin, fout)                       NLZM.cpp:1912-2039
  *   nlzm_codec_free        <- delete[] of the reference's buffers

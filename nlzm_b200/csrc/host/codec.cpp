@@ -3,14 +3,14 @@
 // SURVEY.md §8 f1 (parser consumer + pipeline), f2 (stream writer), f4 (stream reader). C ABI in
 // include/nlzm_codec.h. Restates the reference's encode_file / decode_file drivers
 // (NLZM.cpp:1711-1910, 1912-2039) for a flat input: the whole file goes to HBM once
-// (GpuMatchFinders::Init), candidate blocks come back double-buffered (the GPU computes block N+1
+// (nlzm_mf_set_input), candidate blocks come back double-buffered (the GPU computes block N+1
 // while this thread parses and codes block N), and per chunk of `chunk_size` bytes one frame is
 // written. Ring shifts survive only as the coordinate offset the recent-distance reach test needs.
 //
 // The matcher stage has no CPU implementation here: without a CUDA device nlzm_codec_compress
 // fails with NLZM_CODEC_E_ENGINE.
 #include "../../../include/nlzm_codec.h"
-#include "../../../include/nlzm_mf_shim.hpp"
+#include "../../../include/nlzm_mf.h"
 #include "frame_coder.hpp"
 #include "parser.hpp"
 #include "pipeline.hpp"
@@ -36,24 +36,73 @@ double ms_since(std::chrono::steady_clock::time_point t0) {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 }
 
-// GpuMatchFinders (double-buffered candidate blocks) read directly: a position's steps are folded
-// into the staircase in one pass (Staircase::merge_steps) instead of one Update call per step, and
-// the time spent blocked on a block hand-over is accounted for.
-struct TimedFinders {
-    GpuMatchFinders gpu;
+struct EngineError {
+    std::string what;
+};
+
+// The candidate source: the same double buffering as GpuMatchFinders (include/nlzm_mf_shim.hpp) —
+// while this thread parses and codes block N out of slot N&1, the engine already computes block N+1
+// into the other slot — written against the C ABI directly so that a failing engine call is
+// reported to the caller (the shim keeps the reference's ASSERT -> exit(-1) behaviour). A position's
+// steps are folded into the staircase in one pass (Staircase::merge_steps), and the time spent
+// blocked on a hand-over is accounted for.
+class BlockFeed {
+  public:
+    ~BlockFeed() { close(); }
+    uint64_t steps_served = 0, blocks_fetched = 0;
     double ms_wait = 0;
+
+    void open(const nlzm_mf_config &mc, const uint8_t *in) {
+        int rc = nlzm_mf_create(&mc, &mf_);
+        if (rc) throw EngineError{std::string("engine create failed: ") + nlzm_mf_last_error(nullptr)};
+        check(nlzm_mf_set_input(mf_, in, mc.file_len), "set_input");
+        flen_ = mc.file_len;
+        block_ = mc.max_range;
+        submit_next();
+    }
+    void close() {
+        if (!mf_) return;
+        if (pending_) { nlzm_mf_view v; nlzm_mf_fetch(mf_, slot_ ^ 1, &v); }
+        nlzm_mf_destroy(mf_);
+        mf_ = nullptr;
+    }
     template <class T> void FindAndUpdate(T &st, uint64_t abs_pos) {
-        if (abs_pos >= gpu.cur_end) {
+        if (abs_pos >= view_.end) {
             auto t0 = std::chrono::steady_clock::now();
-            while (abs_pos >= gpu.cur_end) gpu.advance();
+            while (abs_pos >= view_.end) advance();
             ms_wait += ms_since(t0);
         }
-        const uint64_t i = abs_pos - gpu.cur_begin;
-        const nlzm_mf_step *s = gpu.view.steps + gpu.view.offsets[i];
-        const uint32_t n = gpu.view.offsets[i + 1] - gpu.view.offsets[i];
+        const uint64_t i = abs_pos - view_.begin;
+        const nlzm_mf_step *s = view_.steps + view_.offsets[i];
+        const uint32_t n = view_.offsets[i + 1] - view_.offsets[i];
         st.merge_steps(n, [s](uint32_t j) { return NLZM_MF_STEP_DIST(s[j]); }, [s](uint32_t j) { return (uint32_t)s[j].len; });
-        gpu.steps_served += n;
+        steps_served += n;
     }
+
+  private:
+    void check(int rc, const char *what) {
+        if (rc) throw EngineError{std::string("engine ") + what + " failed (rc " + std::to_string(rc) + "): " + nlzm_mf_last_error(mf_)};
+    }
+    void submit_next() {
+        if (next_begin_ >= flen_) return;
+        const uint64_t e = next_begin_ + block_ < flen_ ? next_begin_ + block_ : flen_;
+        check(nlzm_mf_submit(mf_, next_begin_, e, slot_ ^ 1), "submit");
+        next_begin_ = e;
+        pending_ = true;
+    }
+    void advance() {
+        if (!pending_) throw EngineError{"position past the end of the input"};
+        slot_ ^= 1;
+        pending_ = false;
+        check(nlzm_mf_fetch(mf_, slot_, &view_), "fetch");
+        ++blocks_fetched;
+        submit_next();
+    }
+    nlzm_mf *mf_ = nullptr;
+    nlzm_mf_view view_{};
+    uint64_t flen_ = 0, block_ = 0, next_begin_ = 0;
+    int slot_ = 1;
+    bool pending_ = false;
 };
 
 uint32_t read_length_excess(FrameReader &r, StreamModel &m) {
@@ -92,41 +141,25 @@ int compress_impl(const uint8_t *in, uint64_t n, const nlzm_codec_config &cfg, s
     out.push_back((uint8_t)g.frame_bits);
 
     if (n > 0) {
-        // engine: the calls of GpuMatchFinders::Init, with start-up errors returned instead of exit(-1)
-        TimedFinders finders;
-        {
-            nlzm_mf_config mc{};
-            mc.struct_size = sizeof mc;
-            mc.hist_bits = window_bits;
-            mc.file_len = n;
-            mc.device = cfg.device;
-            mc.finder_mask = NLZM_MF_ALL;
-            uint64_t block = cfg.block_len ? cfg.block_len : (g.window > (32u << 20) ? g.window : (32u << 20));
-            if (block > (1ull << 28)) block = 1ull << 28;
-            mc.max_range = block;
-            GpuMatchFinders &gpu = finders.gpu;
-            int rc = nlzm_mf_create(&mc, &gpu.mf);
-            if (rc) return fail(NLZM_CODEC_E_ENGINE, std::string("engine create failed: ") + nlzm_mf_last_error(nullptr));
-            rc = nlzm_mf_set_input(gpu.mf, in, n);
-            if (rc) {
-                std::string why = std::string("engine set_input failed: ") + nlzm_mf_last_error(gpu.mf);
-                gpu.Release();
-                return fail(NLZM_CODEC_E_ENGINE, why);
-            }
-            gpu.flen = n;
-            gpu.block = block;
-            gpu.cur_slot = 1;
-            gpu.submit_next();
-        }
+        BlockFeed finders;
+        nlzm_mf_config mc{};
+        mc.struct_size = sizeof mc;
+        mc.hist_bits = window_bits;
+        mc.file_len = n;
+        mc.device = cfg.device;
+        mc.finder_mask = NLZM_MF_ALL;
+        mc.max_range = cfg.block_len ? cfg.block_len : (g.window > (32u << 20) ? g.window : (32u << 20));
+        if (mc.max_range > (1ull << 28)) mc.max_range = 1ull << 28;
+        finders.open(mc, in);
 
         EncodeCounters ec;
         encode_stream(in, n, g.hist_bits, g.chunk_size, g.feed_size, finders, out, ec);
         st.literals = ec.literals; st.matches = ec.matches; st.reps = ec.reps;
         st.frames = ec.frames; st.parses = ec.parses;
-        st.steps_served = finders.gpu.steps_served;
-        st.engine_blocks = finders.gpu.blocks_fetched;
+        st.steps_served = finders.steps_served;
+        st.engine_blocks = finders.blocks_fetched;
         st.ms_engine_wait = finders.ms_wait;
-        finders.gpu.Release();
+        finders.close();
     }
     out.insert(out.end(), 4, 0);             // a frame with zero ops ends the stream
     st.in_bytes = n;
@@ -221,6 +254,8 @@ int nlzm_codec_compress(const uint8_t *in, uint64_t in_len, const nlzm_codec_con
         if (rc) return rc;
         rc = hand_over(v, out, out_len);
         if (rc) return rc;
+    } catch (const EngineError &e) {
+        return fail(NLZM_CODEC_E_ENGINE, e.what);
     } catch (const std::bad_alloc &) {
         return fail(NLZM_CODEC_E_NOMEM, "out of host memory");
     }
