@@ -80,12 +80,17 @@ class BlockFeed {
     }
 
   private:
+    static constexpr uint64_t kFirstBlockMin = 64u << 10;   // default block 32 Mi -> first block 4 Mi
     void check(int rc, const char *what) {
         if (rc) throw EngineError{std::string("engine ") + what + " failed (rc " + std::to_string(rc) + "): " + nlzm_mf_last_error(mf_)};
     }
     void submit_next() {
         if (next_begin_ >= flen_) return;
-        const uint64_t e = next_begin_ + block_ < flen_ ? next_begin_ + block_ : flen_;
+        // the first block is short so that parsing starts almost at once; it has no window behind it
+        // to rebuild, so the cut costs the engine nothing
+        uint64_t first = block_ / 8 > kFirstBlockMin ? block_ / 8 : kFirstBlockMin;
+        const uint64_t want = next_begin_ == 0 && first < block_ ? first : block_;
+        const uint64_t e = next_begin_ + want < flen_ ? next_begin_ + want : flen_;
         check(nlzm_mf_submit(mf_, next_begin_, e, slot_ ^ 1), "submit");
         next_begin_ = e;
         pending_ = true;

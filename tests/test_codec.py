@@ -86,6 +86,16 @@ def test_compress_matches_engine_fed_reference_stream_emulated(codec_emu, key):
     assert st["literals"] + st["matches"] + st["reps"] > 0 or x.size == 0
 
 
+def test_compress_short_first_block_emulated(codec_emu):
+    """With a large block length the first engine block is cut short (parsing starts early); the
+    stream must not depend on where blocks are cut."""
+    from nlzm_b200 import codec
+    key = "text:150000:24"
+    blob, st = codec.compress(_input("text", 150_000), 24, block_len=600_000, lib=codec_emu, with_stats=True)
+    assert st["engine_blocks"] == 2
+    assert hashlib.sha256(blob).hexdigest() == DIGESTS[key]["sha256"]
+
+
 def test_compress_live_against_reference_parser_and_decoder_emulated(tmp_path, codec_emu):
     """Same comparison made live where oracle/_ref is built: identical to the engine-fed reference
     encoder, restored by the pristine reference decoder. Block length must not matter."""
