@@ -87,8 +87,9 @@ struct ParsedCommand {
     uint32_t value;      // match: distance; repeat: index into the recent distances
 };
 
-// Finders: anything with `template<class T> void FindAndUpdate(T &staircase, uint64_t abs_pos)`
-// (GpuMatchFinders of include/nlzm_mf_shim.hpp).
+// Finders: anything with `template<class T> void FindAndUpdate(T &staircase, uint64_t abs_pos)` that
+// folds the candidates of abs_pos into the staircase — BlockFeed (codec.cpp) over the engine, or
+// GpuMatchFinders of include/nlzm_mf_shim.hpp (which calls Staircase::Update once per step).
 template <class Finders> class SegmentParser {
   public:
     SegmentParser(const uint8_t *text, Finders &finders) : x_(text), finders_(finders), node_(kSegmentMax + 1) {}
