@@ -186,3 +186,24 @@ def test_compress_fuzz_against_reference_parser_emulated(tmp_path, codec_emu, ki
         blob = codec.compress(x, 15, block_len=9_000, lib=codec_emu)
         assert blob == open(ref, "rb").read(), (kind, n)
         assert codec.decompress(blob, lib=codec_emu) == x.tobytes(), (kind, n)
+
+
+def test_compress_is_reentrant_emulated(codec_emu):
+    """Independent inputs may be compressed from several host threads at once (one engine instance
+    each): the sequential parse does not scale inside one stream, replicas across streams do."""
+    import threading
+    from nlzm_b200 import codec
+    keys = ["mixed:120000:20", "text_drift:90000:16", "zeros:40000:15", "random:30000:15"]
+    got = {}
+
+    def work(key):
+        kind, n, hb = key.split(":")
+        got[key] = codec.compress(_input(kind, int(n)), int(hb), block_len=40_000, lib=codec_emu)
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in keys]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for k in keys:
+        assert hashlib.sha256(got[k]).hexdigest() == DIGESTS[k]["sha256"], k
