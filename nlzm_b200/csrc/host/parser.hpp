@@ -141,6 +141,10 @@ template <class Finders> class SegmentParser {
             if ((st.top < kLongEnough || !(p & kSparseMask)) && visible >= 4 + p)
                 finders_.FindAndUpdate(st, start + p);
 
+            // the next position re-extends the longest candidate: one byte past its end, in text this
+            // thread may never have touched (the GPU found the match) — fetch it a position ahead
+            if (st.top > 0) __builtin_prefetch(here + p - st[st.top] + st.top);
+
             uint32_t top = st.top < limit - p ? st.top : limit - p;
             if (top < kLenMin) top = 0;
             while (end < top + p) node_[++end].price = kUnreached;
