@@ -12,6 +12,9 @@
 #define NLZM_HOST_STREAM_MODEL_HPP
 
 #include <stdint.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace nlzm_host {
 
@@ -84,8 +87,17 @@ template <int BITS> struct Table {
         const int16_t *t = kTargets.row[y];
         for (int x = 0; x < N; x++) cum[x] = (uint16_t)(cum[x] + ((int16_t)(t[x] - (int16_t)cum[x]) >> kAdaptShift));
     }
-    // symbol whose slice holds f (decoder)
+    // symbol whose slice holds f (decoder): the number of boundaries cum[1..N-1] that are <= f
     int find(uint32_t f) const {
+#if defined(__SSE2__)
+        if (N >= 8) {                                    // one compare per 8 boundaries; cum[N] = 2^14 > f ends the scan
+            const __m128i vf = _mm_set1_epi16((short)f);
+            __m128i above = _mm_cmpgt_epi16(_mm_loadu_si128((const __m128i *)(cum + 1)), vf);
+            if (N == 8) return __builtin_ctz((unsigned)_mm_movemask_epi8(above)) >> 1;
+            above = _mm_packs_epi16(above, _mm_cmpgt_epi16(_mm_loadu_si128((const __m128i *)(cum + 9)), vf));
+            return __builtin_ctz((unsigned)_mm_movemask_epi8(above));
+        }
+#endif
         int y = 0;
         for (int half = N >> 1; half; half >>= 1)
             if (f >= cum[y + half]) y += half;
