@@ -173,7 +173,37 @@ int compress_impl(const uint8_t *in, uint64_t n, const nlzm_codec_config &cfg, s
     return 0;
 }
 
-int decompress_impl(const uint8_t *in, uint64_t n, std::vector<uint8_t> &out) {
+// Decoder output: raw storage with `size` bytes valid and always >= kSlack bytes of room behind
+// them, so that a literal is one store and a match copies in 8-byte strides without further checks.
+struct OutputSink {
+    static constexpr size_t kSlack = kLenMax + 16;      // longest decodable copy (262 + 5) + one stride
+    uint8_t *p = nullptr;
+    size_t size = 0, cap = 0;
+    ~OutputSink() { free(p); }
+    bool room() {
+        if (cap - size >= kSlack) return true;
+        size_t want = cap + cap / 2 + kSlack + (1u << 16);
+        uint8_t *q = (uint8_t *)realloc(p, want);
+        if (!q) return false;
+        p = q;
+        cap = want;
+        return true;
+    }
+    void literal(uint8_t y) { p[size++] = y; }
+    void copy(size_t dist, size_t len) {
+        uint8_t *to = p + size;
+        const uint8_t *from = to - dist;
+        if (dist >= 8) {
+            for (size_t i = 0; i < len; i += 8) memcpy(to + i, from + i, 8);      // may run up to 7 bytes into the slack
+        } else {
+            for (size_t i = 0; i < len; i++) to[i] = from[i];                      // overlapping: byte by byte
+        }
+        size += len;
+    }
+    uint8_t *release() { uint8_t *r = p; p = nullptr; return r; }
+};
+
+int decompress_impl(const uint8_t *in, uint64_t n, OutputSink &out) {
     if (n < 8) return fail(NLZM_CODEC_E_STREAM, "stream shorter than header + end marker");
     const uint32_t hist_bits = ((uint32_t)in[0] << 8) | in[1], frame_bits = ((uint32_t)in[2] << 8) | in[3];
     if (hist_bits < 10 || hist_bits > 28 || frame_bits < 12 || frame_bits > 20)
@@ -181,20 +211,20 @@ int decompress_impl(const uint8_t *in, uint64_t n, std::vector<uint8_t> &out) {
     StreamModel model;
     model.reset();
     FrameReader frame;
-    out.clear();
     uint64_t at = 4;
     for (;;) {
         int64_t size = frame.begin(in + at, (size_t)(n - at));
         if (size < 0) return fail(NLZM_CODEC_E_STREAM, "malformed frame header at offset " + std::to_string(at));
         if (size == 0) break;
         while (frame.ops_left() > 0) {
+            if (!out.room()) return fail(NLZM_CODEC_E_NOMEM, "out of host memory");
             int kind = frame.get(model.command);
             model.command.adapt(kind);
             if (kind == kLiteral) {
                 int hi = frame.get(model.lit_hi), lo = frame.get(model.lit_lo[hi]);
                 model.lit_hi.adapt(hi);
                 model.lit_lo[hi].adapt(lo);
-                out.push_back((uint8_t)((hi << 4) | lo));
+                out.literal((uint8_t)((hi << 4) | lo));
             } else if (kind == kMatch || kind == kRepeat) {
                 uint32_t dist, len;
                 if (kind == kMatch) {
@@ -222,11 +252,8 @@ int decompress_impl(const uint8_t *in, uint64_t n, std::vector<uint8_t> &out) {
                 }
                 model.recent.remember(dist);
                 if (frame.bad()) break;
-                if (dist > out.size()) return fail(NLZM_CODEC_E_STREAM, "distance reaches before the start of the output");
-                size_t from = out.size() - dist;
-                out.resize(out.size() + len);
-                uint8_t *o = out.data();
-                for (size_t i = 0, to = out.size() - len; i < len; i++) o[to + i] = o[from + i];
+                if (dist > out.size) return fail(NLZM_CODEC_E_STREAM, "distance reaches before the start of the output");
+                out.copy(dist, len);
             } else {
                 return fail(NLZM_CODEC_E_STREAM, "unknown command");
             }
@@ -273,10 +300,13 @@ int nlzm_codec_decompress(const uint8_t *in, uint64_t in_len, uint8_t **out, uin
     *out = nullptr;
     *out_len = 0;
     try {
-        std::vector<uint8_t> v;
-        int rc = decompress_impl(in, in_len, v);
+        OutputSink sink;
+        int rc = decompress_impl(in, in_len, sink);
         if (rc) return rc;
-        return hand_over(v, out, out_len);
+        if (!sink.p && !sink.room()) return fail(NLZM_CODEC_E_NOMEM, "out of host memory");   // empty output still owns a block
+        *out_len = sink.size;
+        *out = sink.release();
+        return 0;
     } catch (const std::bad_alloc &) {
         return fail(NLZM_CODEC_E_NOMEM, "out of host memory");
     }
