@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define NLZM_MF_ABI_VERSION 2
+#define NLZM_MF_ABI_VERSION 3
 
 enum nlzm_mf_finder {
     NLZM_MF_HT2 = 1,      /* MatchFinderHT, 2-byte hash, 1 row   (NLZM.cpp:1750) */
@@ -92,6 +92,10 @@ typedef struct {
     uint64_t kernel_launches;      /* kernels launched by this engine since creation */
     uint64_t tuples_last;          /* candidate tuples produced by the last find */
     float ms_rank, ms_levels, ms_ht, ms_rk, ms_merge, ms_total, ms_d2h;  /* last find, CUDA events */
+    float ms_cross;                /* last find: queries against retained / imported segments */
+    float ms_prepare;              /* last nlzm_mf_prepare (also counted in the ms_total of the find that continues it) */
+    uint32_t segments_queried;     /* last find: retained / imported segments its first block looked into */
+    uint32_t segments_retained;    /* segments kept after the last find */
 } nlzm_mf_stats;
 
 int nlzm_mf_abi_version(void);
@@ -113,10 +117,42 @@ int nlzm_mf_fetch(nlzm_mf *mf, int slot, nlzm_mf_view *out);                    
 
 int nlzm_mf_get_stats(const nlzm_mf *mf, nlzm_mf_stats *out);
 
+/* Matcher state that outlives a call. The reference's BT4 tree persists from one chunk to the next
+ * (MatchFinderBT heads/tree, NLZM.cpp:959-972, shifted but never rebuilt, NLZM.cpp:1024-1031). Here the
+ * persistent state is a list of SEGMENTS: the sorted level array and greater-position pointers of the
+ * last window's worth of positions, kept in HBM after every find. A find whose range starts where
+ * retained segments end queries them instead of re-ranking and re-merging the window behind its
+ * range; any other range is computed from scratch (results are identical either way).
+ *
+ * Position sharding across GPUs (the input is replicated, each engine owns a range):
+ *   1. every engine:  nlzm_mf_prepare(own_begin, own_end)      rank + merge its own range only
+ *   2. every engine:  nlzm_mf_export_segments(...)              descriptors (device pointers + CUDA IPC handles)
+ *   3. engine r:      nlzm_mf_import_segment(...) for the segments of the ranges behind own_begin that lie
+ *                     within the window (copied over NVLink: peer copy in one process, CUDA IPC across processes)
+ *   4. engine r:      nlzm_mf_find(own_begin, own_end, ...)     continues from step 1
+ * No collective is involved; step 3 is a one-sided read of the neighbours' HBM. */
+typedef struct {
+    uint64_t pos_begin, pos_end;            /* absolute positions covered */
+    uint64_t origin;                        /* element positions are relative to this absolute offset */
+    uint64_t n_elems;
+    uint64_t elems_offset_bytes, elems_bytes;   /* the segment's slice inside the exporting engine's allocations */
+    uint64_t ptrs_offset_bytes, ptrs_bytes;
+    const void *elems_alloc, *ptrs_alloc;   /* device pointers (same-process import) */
+    int32_t device;
+    uint32_t flags;                         /* bit 0 / 1: ipc_elems / ipc_ptrs valid */
+    uint8_t ipc_elems[64], ipc_ptrs[64];    /* cudaIpcMemHandle_t of the two allocations (import from another process) */
+} nlzm_mf_segment;
+int nlzm_mf_prepare(nlzm_mf *mf, uint64_t begin, uint64_t end);
+int nlzm_mf_export_segments(nlzm_mf *mf, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out);
+int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *seg, int via_ipc);
+int nlzm_mf_drop_segments(nlzm_mf *mf);
+
 /* Tuning / test knobs (no reference counterpart; results never depend on them):
  *   "ht_margin"      positions before a range for which the HT stage materialises per-position data
  *                    (default: the whole prefix, 12 bytes per position; smaller = less memory, slower look-ups)
- *   "ht_coarse_log"  log2 of the coarse table spacing of the far prefix (default 20) */
+ *   "ht_coarse_log"  log2 of the coarse table spacing of the far prefix (default 20)
+ *   "retain"         0 = forget the segments after every find (default 1)
+ *   "max_segments"   a range with more retained segments than this behind it is computed from scratch (default 8) */
 int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value);
 
 /* Measurement aid (no reference counterpart): with profiling enabled every kernel launch is

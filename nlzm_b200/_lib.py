@@ -32,7 +32,16 @@ class View(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("tuples_last", C.c_uint64)] + \
-               [(n, C.c_float) for n in ("ms_rank", "ms_levels", "ms_ht", "ms_rk", "ms_merge", "ms_total", "ms_d2h")]
+               [(n, C.c_float) for n in ("ms_rank", "ms_levels", "ms_ht", "ms_rk", "ms_merge", "ms_total", "ms_d2h",
+                                          "ms_cross", "ms_prepare")] + \
+               [("segments_queried", C.c_uint32), ("segments_retained", C.c_uint32)]
+
+
+class SegmentDesc(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("pos_begin", "pos_end", "origin", "n_elems", "elems_offset_bytes", "elems_bytes",
+                                          "ptrs_offset_bytes", "ptrs_bytes")] + \
+               [("elems_alloc", C.c_void_p), ("ptrs_alloc", C.c_void_p), ("device", C.c_int32), ("flags", C.c_uint32),
+                ("ipc_elems", C.c_uint8 * 64), ("ipc_ptrs", C.c_uint8 * 64)]
 
 
 class KernelTime(C.Structure):
@@ -41,7 +50,8 @@ class KernelTime(C.Structure):
 
 EXPORTS = ["nlzm_mf_set_option", "nlzm_mf_profile", "nlzm_mf_get_kernel_times", "nlzm_mf_abi_version", "nlzm_mf_get_geometry", "nlzm_mf_create", "nlzm_mf_destroy",
            "nlzm_mf_last_error", "nlzm_mf_set_input", "nlzm_mf_set_input_device", "nlzm_mf_find",
-           "nlzm_mf_find_device", "nlzm_mf_submit", "nlzm_mf_fetch", "nlzm_mf_get_stats"]
+           "nlzm_mf_find_device", "nlzm_mf_submit", "nlzm_mf_fetch", "nlzm_mf_get_stats",
+           "nlzm_mf_prepare", "nlzm_mf_export_segments", "nlzm_mf_import_segment", "nlzm_mf_drop_segments"]
 
 
 def bind_prototypes(L):
@@ -60,6 +70,10 @@ def bind_prototypes(L):
     L.nlzm_mf_submit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int]
     L.nlzm_mf_fetch.argtypes = [C.c_void_p, C.c_int, C.POINTER(View)]
     L.nlzm_mf_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+    L.nlzm_mf_prepare.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    L.nlzm_mf_export_segments.argtypes = [C.c_void_p, C.POINTER(SegmentDesc), C.c_uint32, C.POINTER(C.c_uint32)]
+    L.nlzm_mf_import_segment.argtypes = [C.c_void_p, C.POINTER(SegmentDesc), C.c_int]
+    L.nlzm_mf_drop_segments.argtypes = [C.c_void_p]
     L.nlzm_mf_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
     L.nlzm_mf_profile.argtypes = [C.c_int]
     L.nlzm_mf_get_kernel_times.argtypes = [C.POINTER(KernelTime), C.c_uint32, C.POINTER(C.c_uint32)]
@@ -76,6 +90,6 @@ def load():
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                "(nvcc, sm_100a). There is no CPU fallback.")
         _lib = bind_prototypes(C.CDLL(LIB_PATH))
-        if _lib.nlzm_mf_abi_version() != 2:
+        if _lib.nlzm_mf_abi_version() != 3:
             raise RuntimeError("libnlzm_mf.so ABI version mismatch")
     return _lib

@@ -96,7 +96,19 @@ struct DcParams {
     const u32 *part;     // merge-path split per output tile (merge levels)
     PtrEntry *ptr;       // indexed by universe-relative position
     TupleSink sink;
+    u32 n_valid;         // universe-relative positions >= n_valid lie past own_e ("pads", present only so that the
+                         // ranks of the last own positions are exact): they sort behind everything and are never adopted
+    // cross pass against a RETAINED segment (sorted array + pointers of an earlier find, possibly computed on another
+    // GPU, with its own rank universe): the left side is the segment, the right side one sorted block of this find
+    const Elem *seg;     // retained segment, sorted by suffix order
+    const PtrEntry *seg_ptr;   // its pointers, indexed by position relative to seg_u0
+    u64 seg_u0;          // absolute offset its positions are relative to
+    u64 seg_last;        // absolute offset of its last position (window pruning)
+    u32 seg_len;         // elements in it
+    Elem *own;           // right side: a sorted block of this find (best lengths are written back)
+    u32 own_len;
 };
+#define NLZM_RANK_PAD 0xFFFFFFFFu
 
 DEV void dc_emit(const DcParams &p, u64 a_abs, u32 dist, u32 len) {
     if (dist <= p.g.W - 1 && len >= match_min(dist)) tuple_append(p.sink, (u32)(a_abs - p.own_b), dist, len);
@@ -205,7 +217,7 @@ DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
     const u64 x_end = p.g.flen + NLZM_X_PAD;                 // bytes [flen, x_end) are zero padding
     for (u32 i = tid; i < NLZM_BASE_TEXT; i += NLZM_BASE_THREADS) s.text[i] = (abs0 + i < x_end) ? p.x[abs0 + i] : (u8)0;
     for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
-        s.rnk[i] = p.rank[t0 + i];
+        s.rnk[i] = (t0 + i) < p.n_valid ? p.rank[t0 + i] : NLZM_RANK_PAD;
         s.arr[0][i] = (u16)i;
         s.pg[i] = NLZM_L16_NONE;
         s.ng[i] = NLZM_L16_NONE;
@@ -307,7 +319,7 @@ DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
             if (r_len == 0) continue;
             const u32 pos = A[i], u = s.cor[i];
             if (u > 0) { const u32 r = A[r_beg + u - 1]; const u32 o = s.pg[pos]; if (o == NLZM_L16_NONE || base_less(s, o, r)) s.pg[pos] = (u16)r; }
-            if (u < r_len) { const u32 r = A[r_beg + u]; const u32 o = s.ng[pos]; if (o == NLZM_L16_NONE || base_less(s, r, o)) s.ng[pos] = (u16)r; }
+            if (u < r_len) { const u32 r = A[r_beg + u]; const u32 o = s.ng[pos]; if (s.rnk[r] != NLZM_RANK_PAD && (o == NLZM_L16_NONE || base_less(s, r, o))) s.ng[pos] = (u16)r; }
         }
         NLZM_CTA_SYNC();
         cur ^= 1;
@@ -421,12 +433,13 @@ DEV u32 elem_prefix_lcp(const Elem &a, const Elem &b) {
 }
 
 // full lcp of the suffixes behind two elements (prefixes first, text beyond), capped at lim
-DEV u32 elem_pair_lcp(const DcParams &p, const Elem &a, const Elem &b, u32 lim) {
+DEV u32 elem_pair_lcp2(const DcParams &p, const Elem &a, u64 a_u0, const Elem &b, u64 b_u0, u32 lim) {
     u32 l = elem_prefix_lcp(a, b);
     if (l >= NLZM_ELEM_PREFIX && lim > NLZM_ELEM_PREFIX)
-        l = NLZM_ELEM_PREFIX + lcp_cap(p.x, p.u0 + (u32)a.key + NLZM_ELEM_PREFIX, p.u0 + (u32)b.key + NLZM_ELEM_PREFIX, lim - NLZM_ELEM_PREFIX);
+        l = NLZM_ELEM_PREFIX + lcp_cap(p.x, a_u0 + (u32)a.key + NLZM_ELEM_PREFIX, b_u0 + (u32)b.key + NLZM_ELEM_PREFIX, lim - NLZM_ELEM_PREFIX);
     return l < lim ? l : lim;
 }
+DEV u32 elem_pair_lcp(const DcParams &p, const Elem &a, const Elem &b, u32 lim) { return elem_pair_lcp2(p, a, p.u0, b, p.u0, lim); }
 
 // Walk one greater-position chain of the left half. The first element is a rank neighbour whose element
 // (prefix, link lcp) sits in shared memory; the lcp with every further chain element follows from the
@@ -434,10 +447,11 @@ DEV u32 elem_pair_lcp(const DcParams &p, const Elem &a, const Elem &b, u32 lim) 
 // read per hop, none at all when the chain ends at the neighbour.
 // (dom_c, dom_l): the other side's first candidate; anything it dominates (nearer and at least as long) would
 // only be merged away later, so it is not queued.
+// (ptr, delta): the pointer table of the chain's side and how far its position origin lies before p.u0 (0 inside one find)
 DEV void dc_walk(const DcParams &p, const Elem &ea, u64 a_abs, u32 best_in, const Elem *first, u32 first_l, bool left,
-                 u32 dom_c, u32 dom_l, u32 &new_best) {
+                 u32 dom_c, u32 dom_l, u32 &new_best, const PtrEntry *__restrict__ ptr, u32 delta) {
     if (!first) return;
-    const u32 a_rel = (u32)ea.key;
+    const u32 a_rel = (u32)ea.key + delta;
     u32 c = (u32)first->key;
     u32 l = first_l;
     u32 link = left ? elem_lpg(first->tail) : elem_lng(first->tail);
@@ -450,12 +464,12 @@ DEV void dc_walk(const DcParams &p, const Elem &ea, u64 a_abs, u32 best_in, cons
         if (l > new_best) new_best = l;
         const u32 l_next = l < link ? l : link;                // lcp never grows along the chain
         if (l_next <= best_in) break;                          // the chain ends here without touching memory
-        if (!have_entry) en = p.ptr[c];                        // the neighbour's pointer (its link lcp came with the element)
+        if (!have_entry) en = ptr[c];                          // the neighbour's pointer (its link lcp came with the element)
         const u64 k = left ? en.pg : en.ng;
         if (k == (left ? NLZM_PG_NONE : NLZM_NG_NONE)) break;
         c = (u32)k;
         l = l_next;
-        en = p.ptr[c];
+        en = ptr[c];
         have_entry = true;
         link = left ? en.lpg : en.lng;
     }
@@ -561,9 +575,13 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         const Elem *fl = (l0 + li > 0) ? &el[li] : nullptr, *fr = (l0 + li < s.l_len) ? &el[li + 1] : nullptr;
         const u32 ll = fl ? elem_pair_lcp(p, ea, *fl, cap) : 0u, lr = fr ? elem_pair_lcp(p, ea, *fr, cap) : 0u;
         const u32 cl = fl ? (u32)fl->key : 0u, cr = fr ? (u32)fr->key : 0u;
-        dc_walk(p, ea, a_abs, best_in, fl, ll, true, cr, lr > best_in ? lr : 0u, nb);
-        dc_walk(p, ea, a_abs, best_in, fr, lr, false, cl, ll > best_in ? ll : 0u, nb);
-        if (nb != best_in) e.tail = elem_set_best(ea.tail, nb);
+        dc_walk(p, ea, a_abs, best_in, fl, ll, true, cr, lr > best_in ? lr : 0u, nb, p.ptr, 0u);
+        dc_walk(p, ea, a_abs, best_in, fr, lr, false, cl, ll > best_in ? ll : 0u, nb, p.ptr, 0u);
+        if (nb != best_in) {
+            e.tail = elem_set_best(ea.tail, nb);
+            // query-only pass: nothing is stored, but the next pass over the same elements should know this length
+            if (p.cross) ((Elem *)p.cur)[s.r_beg + r0 + (src[o] - (nl + 2))].tail = e.tail;
+        }
     }
     NLZM_CTA_SYNC();
 
@@ -603,7 +621,7 @@ DEV void dc_link_body(const DcParams &p, u64 idx64) {
     }
     if (u < s.r_len) {
         const Elem r = p.cur[s.r_beg + u];
-        if (r.key < en.ng) {
+        if (r.key < en.ng && (u32)(r.key >> 32) != NLZM_RANK_PAD) {
             const u64 left_in_file = p.g.flen - (p.u0 + (u32)r.key);
             en.ng = r.key;
             en.lng = (u16)elem_pair_lcp(p, e, r, left_in_file < NLZM_MATCH_MAX ? (u32)left_in_file : NLZM_MATCH_MAX);
@@ -617,3 +635,133 @@ DEV void dc_link_body(const DcParams &p, u64 idx64) {
     }
 }
 NLZM_KERNEL_1D(dc_link, DcParams)
+
+// ================================================================================================
+// cross pass against a retained segment
+// ================================================================================================
+// A find keeps its final sorted blocks and pointers ("segments"); a later find whose range follows does not
+// re-rank and re-merge the window behind it but queries those segments. Ranks of different finds (or GPUs) are
+// not comparable, so the merge order comes from the suffixes themselves: the carried 18-byte prefixes first, the
+// text beyond them when those tie. Both sides are sorted by an order that refines "first 264 symbols, end of file
+// below every byte", so merging them under that order is well defined; ties put the (earlier) segment side first,
+// which is what the rank order does with equal ranks.
+
+// does segment element l go before own element r?
+DEV bool x_left_first(const DcParams &p, const Elem &l, const Elem &r) {
+    u64 d = l.p0 ^ r.p0;
+    if (d) { const u32 sh = (u32)nlzm_ctz64(d) & ~7u; return ((l.p0 >> sh) & 0xFF) < ((r.p0 >> sh) & 0xFF); }
+    d = l.p1 ^ r.p1;
+    if (d) { const u32 sh = (u32)nlzm_ctz64(d) & ~7u; return ((l.p1 >> sh) & 0xFF) < ((r.p1 >> sh) & 0xFF); }
+    d = (l.tail ^ r.tail) & 0xFFFFull;
+    if (d) { const u32 sh = (u32)nlzm_ctz64(d) & ~7u; return ((l.tail >> sh) & 0xFF) < ((r.tail >> sh) & 0xFF); }
+    // 18 equal bytes (bytes past the end of the file read as zero padding). r is the later position: it reaches
+    // the end of the file first, and a suffix that ends sorts below one that goes on.
+    const u64 pl = p.seg_u0 + (u32)l.key, pr = p.u0 + (u32)r.key;
+    const u64 left_r = p.g.flen - pr;
+    if (left_r <= NLZM_ELEM_PREFIX) return false;
+    const u32 lim = left_r < NLZM_MATCH_MAX ? (u32)left_r : NLZM_MATCH_MAX;
+    const u32 m = NLZM_ELEM_PREFIX + lcp_cap(p.x, pl + NLZM_ELEM_PREFIX, pr + NLZM_ELEM_PREFIX, lim - NLZM_ELEM_PREFIX);
+    if (m < lim) return p.x[pl + m] < p.x[pr + m];
+    return lim == NLZM_MATCH_MAX;               // equal to the full depth: segment side first; r ended: r first
+}
+
+DEV u32 x_merge_path(const DcParams &p, const Elem *L, u32 l_len, const Elem *R, u32 r_len, u32 d) {
+    u32 lo = d > r_len ? d - r_len : 0, hi = d < l_len ? d : l_len;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (x_left_first(p, L[mid], R[d - 1 - mid])) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+DEV void dc_xpartition_body(const DcParams &p, u64 j) {
+    const u32 o = (u32)j * NLZM_MT_TILE;
+    ((u32 *)p.part)[j] = x_merge_path(p, p.seg, p.seg_len, p.own, p.own_len, o);
+}
+NLZM_KERNEL_1D(dc_xpartition, DcParams)
+
+// Same tile scheme as dc_merge_tile_cta, query only: the own elements look up their two neighbours in the
+// segment and walk the segment's chains; nothing is stored except the best lengths they reach.
+DEV void dc_xmerge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
+    Elem *el = (Elem *)smem;
+    u16 *src = (u16 *)(smem + (NLZM_MT_TILE + 2) * 32);
+    u16 *lcnt = src + NLZM_MT_TILE;
+    u16 *act = lcnt + 2 * NLZM_MT_TILE;
+    u32 *act_n = (u32 *)(act + NLZM_MT_TILE);
+
+    const u32 total = p.seg_len + p.own_len;
+    const u32 o0 = bid * NLZM_MT_TILE;
+    const u32 o1 = (o0 + NLZM_MT_TILE) < total ? (o0 + NLZM_MT_TILE) : total;
+    const u32 cnt = o1 - o0;
+    const u32 l0 = p.part[bid];
+    const u32 l1 = (o1 < total) ? p.part[bid + 1] : p.seg_len;
+    const u32 r0 = o0 - l0, r1 = o1 - l1;
+    const u32 nl = l1 - l0, nr = r1 - r0;
+    if (nr == 0) return;                                        // no own element in this tile: nothing to ask
+    Elem *SL = el + 1;
+    Elem *SR = el + nl + 2;
+    {
+        const V16 *GL = (const V16 *)p.seg, *GR = (const V16 *)p.own;
+        V16 *S = (V16 *)el;
+        for (u32 c = tid; c < (nl + 2) * 2; c += NLZM_MT_THREADS) {
+            const i64 gi = (i64)l0 + (i64)(c >> 1) - 1;
+            if (gi >= 0 && gi < (i64)p.seg_len) S[c] = GL[gi * 2 + (c & 1)];
+        }
+        V16 *S2 = (V16 *)SR;
+        for (u32 c = tid; c < nr * 2; c += NLZM_MT_THREADS) S2[c] = GR[(u64)r0 * 2 + c];
+    }
+    if (tid == 0) *act_n = 0;
+    NLZM_CTA_SYNC();
+    {
+        const u32 t_d = tid * NLZM_MT_ITEMS < cnt ? tid * NLZM_MT_ITEMS : cnt;
+        const u32 t_e = t_d + NLZM_MT_ITEMS < cnt ? t_d + NLZM_MT_ITEMS : cnt;
+        u32 li = t_d < t_e ? x_merge_path(p, SL, nl, SR, nr, t_d) : 0u, ri = t_d - li;
+        for (u32 o = t_d; o < t_e; o++) {
+            const bool take_l = (ri >= nr) || (li < nl && x_left_first(p, SL[li], SR[ri]));
+            if (take_l) {
+                src[o] = (u16)(1 + li);
+                ++li;
+            } else {
+                src[o] = (u16)(nl + 2 + ri);
+                lcnt[o] = (u16)li;
+                ++ri;
+            }
+        }
+    }
+    NLZM_CTA_SYNC();
+    const u32 delta = (u32)(p.u0 - p.seg_u0);
+    for (u32 o = tid; o < cnt; o += NLZM_MT_THREADS) {
+        const u32 slot = src[o];
+        if (slot < nl + 2) continue;
+        const Elem &e = el[slot];
+        const u64 a_abs = p.u0 + (u32)e.key;
+        u32 cap;
+        const u32 best_in = elem_best(e.tail);
+        if (!dc_query_cap(p, a_abs, cap) || best_in >= cap || a_abs - p.seg_last > p.g.W - 1) continue;
+        const u32 li = lcnt[o];
+        bool want = false;
+        if (l0 + li > 0) { u32 l = elem_prefix_lcp(e, el[li]); l = l < cap ? l : cap; want |= (l > best_in) || (l >= NLZM_ELEM_PREFIX && cap > NLZM_ELEM_PREFIX); }
+        if (l0 + li < p.seg_len) { u32 l = elem_prefix_lcp(e, el[li + 1]); l = l < cap ? l : cap; want |= (l > best_in) || (l >= NLZM_ELEM_PREFIX && cap > NLZM_ELEM_PREFIX); }
+        if (want) act[nlzm_atomic_add(act_n, 1u)] = (u16)o;
+    }
+    NLZM_CTA_SYNC();
+    const u32 n_act = *act_n;
+    for (u32 k = tid; k < n_act; k += NLZM_MT_THREADS) {
+        const u32 o = act[k];
+        const u32 slot = src[o];
+        const Elem ea = el[slot];
+        const u64 a_abs = p.u0 + (u32)ea.key;
+        u32 cap = 0;
+        dc_query_cap(p, a_abs, cap);
+        const u32 best_in = elem_best(ea.tail);
+        const u32 li = lcnt[o];
+        u32 nb = best_in;
+        const Elem *fl = (l0 + li > 0) ? &el[li] : nullptr, *fr = (l0 + li < p.seg_len) ? &el[li + 1] : nullptr;
+        const u32 ll = fl ? elem_pair_lcp2(p, ea, p.u0, *fl, p.seg_u0, cap) : 0u, lr = fr ? elem_pair_lcp2(p, ea, p.u0, *fr, p.seg_u0, cap) : 0u;
+        const u32 cl = fl ? (u32)fl->key : 0u, cr = fr ? (u32)fr->key : 0u;
+        dc_walk(p, ea, a_abs, best_in, fl, ll, true, cr, lr > best_in ? lr : 0u, nb, p.seg_ptr, delta);
+        dc_walk(p, ea, a_abs, best_in, fr, lr, false, cl, ll > best_in ? ll : 0u, nb, p.seg_ptr, delta);
+        if (nb != best_in) p.own[r0 + (slot - (nl + 2))].tail = elem_set_best(ea.tail, nb);
+    }
+}
+NLZM_KERNEL_CTA_OCC(dc_xmerge_tile, DcParams, NLZM_MT_THREADS, 3)

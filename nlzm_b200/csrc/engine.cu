@@ -18,6 +18,7 @@
 #include <atomic>
 #include <map>
 #include <mutex>
+#include <memory>
 #include <new>
 #include <string>
 #include <thread>
@@ -36,41 +37,53 @@ extern "C" unsigned long long *nlzm_emu_stats() { return nlzm_stats; }
 static std::atomic<unsigned long long> g_launches{0};
 struct KernelProf {
     struct Pending { const char *name; cudaEvent_t a, b; };
-    bool on = false;
+    std::atomic<bool> on{false};
     std::mutex mu;
-    std::vector<Pending> pending;
     std::map<std::string, std::pair<u64, double>> acc;     // name -> (launches, ms)
-    void resolve() {                                        // call after the stream is synchronized
-        std::lock_guard<std::mutex> l(mu);
-        for (auto &p : pending) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, p.a, p.b);
-            auto &e = acc[p.name];
-            e.first += 1;
-            e.second += ms;
-            cudaEventDestroy(p.a);
-            cudaEventDestroy(p.b);
-        }
-        pending.clear();
-    }
 };
 static KernelProf g_prof;
+// launches of one find are issued by one host thread: the begin/end pairing stays inside that thread
+static thread_local std::vector<KernelProf::Pending> tl_pending;
+static void prof_resolve() {                               // call after the stream is synchronized
+    if (tl_pending.empty()) return;
+    std::lock_guard<std::mutex> l(g_prof.mu);
+    for (auto &p : tl_pending) {
+        float ms = 0;
+        if (p.b && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            auto &e = g_prof.acc[p.name];
+            e.first += 1;
+            e.second += ms;
+        }
+        cudaEventDestroy(p.a);
+        if (p.b) cudaEventDestroy(p.b);
+    }
+    tl_pending.clear();
+}
 void nlzm_launch_begin(const char *name, cudaStream_t st) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    if (!g_prof.on) return;
+    if (!g_prof.on.load(std::memory_order_relaxed)) return;
     KernelProf::Pending p;
     p.name = name;
+    p.b = nullptr;
     cudaEventCreate(&p.a);
-    cudaEventCreate(&p.b);
     cudaEventRecord(p.a, st);
-    std::lock_guard<std::mutex> l(g_prof.mu);
-    g_prof.pending.push_back(p);
+    tl_pending.push_back(p);
 }
 void nlzm_launch_end(cudaStream_t st) {
-    if (!g_prof.on) return;
-    std::lock_guard<std::mutex> l(g_prof.mu);
-    cudaEventRecord(g_prof.pending.back().b, st);
+    if (tl_pending.empty() || tl_pending.back().b) return;
+    cudaEventCreate(&tl_pending.back().b);
+    cudaEventRecord(tl_pending.back().b, st);
 }
+
+// CUDA event that cannot leak on an early return
+struct Ev {
+    cudaEvent_t e = nullptr;
+    Ev() { cudaEventCreate(&e); }
+    ~Ev() { if (e) cudaEventDestroy(e); }
+    Ev(const Ev &) = delete;
+    Ev &operator=(const Ev &) = delete;
+    operator cudaEvent_t() const { return e; }
+};
 
 static std::string g_create_error;
 
@@ -104,12 +117,34 @@ struct Slot {
     int status = 0;
 };
 
+// A retained segment: one sorted block of a finished stage T (level array + pointers). A later find
+// whose range follows queries it instead of re-ranking and re-merging the window behind its range
+// (dc_xmerge_tile); it can also come from another engine / GPU (nlzm_mf_import_segment).
+struct SegBufs {
+    nlzm_mf *owner = nullptr;
+    DevBuf el, ptr;
+    ~SegBufs();
+};
+struct Segment {
+    std::shared_ptr<SegBufs> bufs;
+    u64 u0 = 0;          // element positions are relative to this absolute offset
+    u64 elem_off = 0;    // first element inside bufs->el
+    u32 n_elems = 0;     // valid elements (positions past the producing find's range are cut off)
+    u64 ptr_pos0 = 0;    // absolute position of bufs->ptr[0]
+    u64 pos_b = 0, pos_e = 0;    // absolute positions covered
+    const Elem *elems() const { return bufs->el.as<Elem>() + elem_off; }
+    Elem *elems_rw() const { return bufs->el.as<Elem>() + elem_off; }
+    const PtrEntry *ptrs() const {       // indexable by (position - u0)
+        return (const PtrEntry *)((uintptr_t)bufs->ptr.p - (uintptr_t)((ptr_pos0 - u0) * sizeof(PtrEntry)));
+    }
+};
+
 struct nlzm_mf {
     Geom g;
     int device = 0;
     u32 mask = NLZM_MF_ALL;
     u64 max_range = 0;
-    cudaStream_t st = 0;
+    cudaStream_t st = 0, st_copy = 0;
     DevBuf x;
     bool have_input = false;
 
@@ -126,9 +161,20 @@ struct nlzm_mf {
     u64 ht_margin = NLZM_HT_MARGIN;        // options (nlzm_mf_set_option): tuning / test knobs
     u32 ht_coarse_log = NLZM_HT_COARSE_LOG;
     bool rk_all_hits = false, rk_overflowed = false;
+    bool retain = true;                    // option "retain": keep the sorted blocks of a find for the next one
+    u32 max_segments = 8;                  // option "max_segments": more retained segments than this behind a range => halo mode
+
+    std::vector<Segment> segs;             // retained, ascending by position
+    std::vector<Segment> fresh;            // sorted blocks of the find in progress (own universe)
+    u64 fresh_u0 = 0;
+    bool prepared = false;                 // nlzm_mf_prepare ran stages S/T for [prep_b, prep_e): find continues from there
+    u64 prep_b = 0, prep_e = 0;
+    std::vector<DevBuf> pool;              // level-array / pointer buffers waiting to be reused
+    std::mutex pool_mu;
 
     Slot slot[2];
-    std::mutex mu;
+    std::mutex mu;                         // one find computes at a time
+    std::mutex stats_mu;
     std::string err;
     nlzm_mf_stats stats{};
 
@@ -150,6 +196,36 @@ struct nlzm_mf {
         }
         b.bytes = want;
         return 0;
+    }
+    // big level-array / pointer buffers move in and out of retained segments: take a fitting one from the pool first
+    int ensure_pooled(DevBuf &b, size_t bytes) {
+        if (bytes <= b.bytes) return 0;
+        {
+            std::lock_guard<std::mutex> l(pool_mu);
+            int best = -1;
+            for (size_t i = 0; i < pool.size(); i++)
+                if (pool[i].bytes >= bytes && (best < 0 || pool[i].bytes < pool[(size_t)best].bytes)) best = (int)i;
+            if (best >= 0) {
+                std::swap(b, pool[(size_t)best]);
+                if (!pool[(size_t)best].p) pool.erase(pool.begin() + best);
+                return 0;
+            }
+        }
+        return ensure(b, bytes);
+    }
+    void to_pool(DevBuf &b) {
+        if (!b.p) return;
+        std::lock_guard<std::mutex> l(pool_mu);
+        if (pool.size() >= 6) {                       // keep the largest few
+            size_t small = 0;
+            for (size_t i = 1; i < pool.size(); i++) if (pool[i].bytes < pool[small].bytes) small = i;
+            if (pool[small].bytes < b.bytes) std::swap(pool[small], b);
+            cudaFree(b.p);
+        } else {
+            pool.push_back(b);
+        }
+        b.p = nullptr;
+        b.bytes = 0;
     }
     void release(DevBuf &b) {
         if (b.p) cudaFree(b.p);
@@ -175,12 +251,22 @@ struct nlzm_mf {
         return s;
     }
 
-    int stage_bt4(u64 own_b, u64 own_e);
+    bool covered_by_segments(u64 b, std::vector<Segment> &use) const;
+    int stage_bt4_own(u64 own_b, u64 own_e, u64 u0);
+    int stage_bt4_cross(u64 own_b, u64 own_e, const std::vector<Segment> &behind);
+    void retain_fresh(u64 own_e);
     int stage_ht(u64 own_b, u64 own_e, const HtCfg &c);
     int stage_rk(u64 own_b, u64 own_e);
     int stage_merge(u64 own_b, u64 own_e, Slot &s);
+    int compute(u64 b, u64 e, Slot &s);
     int find_impl(u64 b, u64 e, int slot, bool to_host);
+    int prepare_impl(u64 b, u64 e);
 };
+
+SegBufs::~SegBufs() {
+    if (owner) { owner->to_pool(el); owner->to_pool(ptr); }
+    else { if (el.p) cudaFree(el.p); if (ptr.p) cudaFree(ptr.p); }
+}
 
 static inline u32 bits_for(u64 v) {
     u32 b = 0;
@@ -188,28 +274,44 @@ static inline u32 bits_for(u64 v) {
     return b;
 }
 
+// Retained segments that cover the window behind position b without a gap, nearest first.
+bool nlzm_mf::covered_by_segments(u64 b, std::vector<Segment> &use) const {
+    use.clear();
+    const u64 need = b > (u64)(g.W - 1) ? b - (g.W - 1) : 0;
+    u64 at = b;
+    while (at > need) {
+        const Segment *hit = nullptr;
+        for (const Segment &s : segs) if (s.pos_e == at && s.pos_b < at) { hit = &s; break; }
+        if (!hit) return false;
+        use.push_back(*hit);
+        if (use.size() > max_segments) return false;
+        at = hit->pos_b;
+    }
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
-// Stage S + T (+ the 2..3-byte bucket-collision candidates of small windows)
+// Stage S + T over the universe [u0, own_e + pad) (+ the 2..3-byte bucket-collision candidates of small windows)
 // ------------------------------------------------------------------------------------------------
-int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
-    const u64 u0 = own_b > (u64)(g.W - 1) ? own_b - (g.W - 1) : 0;
+int nlzm_mf::stage_bt4_own(u64 own_b, u64 own_e, u64 u0) {
+    fresh.clear();
+    fresh_u0 = u0;
     const u64 u1 = own_e + 1024 < g.flen ? own_e + 1024 : g.flen;
     const u64 n = u1 - u0;
     if (n < 2) return 0;
     CKI(ensure(k64[0], n * 8)); CKI(ensure(k64[1], n * 8));
     CKI(ensure(v32[0], n * 4)); CKI(ensure(v32[1], n * 4));
     CKI(ensure(rank, n * 4)); CKI(ensure(aux0, n * 4)); CKI(ensure(aux1, n * 4));
-    CKI(ensure(ptr, n * sizeof(PtrEntry)));
+    CKI(ensure_pooled(ptr, n * sizeof(PtrEntry)));
     CKI(ensure_prim(n));
     u64 *sum_dev = scalars.as<u64>();
 
-    cudaEvent_t ev0, ev1, ev2;
-    cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&ev2);
+    Ev ev0, ev1, ev2;
     cudaEventRecord(ev0, st);
 
     // --- S: prefix doubling 8 -> 16 -> ... -> >= 264 bytes; rounds after the first only re-sort the
     //        positions whose group is still ambiguous. Scratch comes out of the (not yet used) level arrays.
-    CKI(ensure(el[0], n * sizeof(Elem))); CKI(ensure(el[1], n * sizeof(Elem)));
+    CKI(ensure_pooled(el[0], n * sizeof(Elem))); CKI(ensure_pooled(el[1], n * sizeof(Elem)));
     u32 *scratch = el[1].as<u32>();
     u32 *new_grp = scratch, *act_flag = scratch + n, *act_idx = scratch + 2 * n;
     u32 *grp_buf[2] = {scratch + 3 * n, scratch + 4 * n}, *pos_buf[2] = {scratch + 5 * n, scratch + 6 * n};
@@ -253,13 +355,14 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
     // --- T: first NLZM_BASE_LOG levels in shared memory, then one merge-path pass per level
     const u64 tiles = (n + NLZM_MT_TILE - 1) / NLZM_MT_TILE;
     CKI(ensure(part, (tiles + 2) * 4));
-    DcParams dp;
+    DcParams dp{};
     dp.x = x.as<u8>();
     dp.g = g;
     dp.u0 = u0;
     dp.own_b = own_b;
     dp.own_e = own_e;
     dp.n = (u32)n;
+    dp.n_valid = (u32)(own_e - u0);
     dp.h = 0;
     dp.rank = rank.as<u32>();
     dp.cur = nullptr;
@@ -285,7 +388,7 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
         cur ^= 1;
     }
     // ... then every window-sized block queries the block before it (two passes: even and odd pairs);
-    // these passes store nothing: no level above them exists
+    // these passes store nothing but the best lengths: no level above them exists
     if (n > (u64)g.W && (u64)g.W >= NLZM_BASE_TILE) {
         for (u32 parity = 0; parity < 2; parity++) {
             const u64 origin = (u64)parity * g.W;
@@ -328,8 +431,82 @@ int nlzm_mf::stage_bt4(u64 own_b, u64 own_e) {
     CK(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&stats.ms_rank, ev0, ev1);
     cudaEventElapsedTime(&stats.ms_levels, ev1, ev2);
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+
+    // The final level array (sorted window-sized blocks, or one sorted array) and the pointers become segments.
+    // Positions past own_e carry the pad rank and sit at the end of their block: they are cut off.
+    auto bufs = std::make_shared<SegBufs>();
+    bufs->owner = this;
+    std::swap(bufs->el, el[cur]);
+    std::swap(bufs->ptr, ptr);
+    const u64 n_valid = own_e - u0;
+    const u64 blk = n > (u64)g.W ? (u64)g.W : n;
+    for (u64 o = 0; o < n_valid; o += blk) {
+        Segment sg;
+        sg.bufs = bufs;
+        sg.u0 = u0;
+        sg.elem_off = o;
+        sg.n_elems = (u32)((n_valid - o) < blk ? (n_valid - o) : blk);
+        sg.ptr_pos0 = u0;
+        sg.pos_b = u0 + o;
+        sg.pos_e = sg.pos_b + sg.n_elems;
+        fresh.push_back(sg);
+    }
     return 0;
+}
+
+// The first block of the own universe queries the retained segments behind it, nearest first (a longer
+// match further back only counts if nothing nearer is at least as long: best lengths carry over).
+int nlzm_mf::stage_bt4_cross(u64 own_b, u64 own_e, const std::vector<Segment> &behind) {
+    stats.segments_queried = 0;
+    if (fresh.empty() || behind.empty()) return 0;
+    const Segment &own = fresh.front();
+    Ev ev0, ev1;
+    cudaEventRecord(ev0, st);
+    for (const Segment &sg : behind) {
+        if (sg.n_elems == 0) continue;
+        const u64 total = (u64)sg.n_elems + own.n_elems;
+        const u64 tiles = (total + NLZM_MT_TILE - 1) / NLZM_MT_TILE;
+        CKI(ensure(part, (tiles + 2) * 4));
+        DcParams cp{};
+        cp.x = x.as<u8>();
+        cp.g = g;
+        cp.u0 = own.u0;
+        cp.own_b = own_b;
+        cp.own_e = own_e;
+        cp.part = part.as<u32>();
+        cp.sink = sink();
+        cp.cross = 2;
+        cp.seg = sg.elems();
+        cp.seg_ptr = sg.ptrs();
+        cp.seg_u0 = sg.u0;
+        cp.seg_last = sg.pos_e - 1;
+        cp.seg_len = sg.n_elems;
+        cp.own = own.elems_rw();
+        cp.own_len = own.n_elems;
+        stats.segments_queried += 1;
+        launch_dc_xpartition(cp, tiles, st);
+        CKI(launch_dc_xmerge_tile(cp, tiles, NLZM_MT_SMEM, st));
+    }
+    cudaEventRecord(ev1, st);
+    CK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&stats.ms_cross, ev0, ev1);
+    return 0;
+}
+
+// after a find: its blocks join the retained list; whatever a range starting at own_e could not reach goes
+void nlzm_mf::retain_fresh(u64 own_e) {
+    if (!retain) { fresh.clear(); segs.clear(); return; }
+    for (Segment &sg : fresh) {
+        bool dup = false;
+        for (const Segment &o : segs) if (o.pos_b == sg.pos_b && o.pos_e == sg.pos_e) dup = true;
+        if (!dup) segs.push_back(sg);
+    }
+    fresh.clear();
+    const u64 keep_from = own_e > (u64)(g.W - 1) ? own_e - (g.W - 1) : 0;
+    std::vector<Segment> kept;
+    for (Segment &sg : segs) if (sg.pos_e > keep_from && sg.pos_e <= own_e) kept.push_back(sg);
+    segs.swap(kept);
+    stats.segments_retained = (u32)segs.size();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -502,32 +679,39 @@ int nlzm_mf::stage_merge(u64 own_b, u64 own_e, Slot &s) {
     return 0;
 }
 
-int nlzm_mf::find_impl(u64 b, u64 e, int si, bool to_host) {
-    std::lock_guard<std::mutex> lock(mu);
-    if (!have_input) return fail(NLZM_MF_E_STATE, "find before set_input");
-    if (si < 0 || si > 1) return fail(NLZM_MF_E_ARG, "slot must be 0 or 1");
-    if (b > e || e > g.flen) return fail(NLZM_MF_E_ARG, "bad range");
-    if (e - b > (1ull << 28)) return fail(NLZM_MF_E_ARG, "range larger than 2^28 positions: split it");
-    if (e - b > max_range) return fail(NLZM_MF_E_ARG, "range larger than config.max_range");
-#ifndef NLZM_EMU
-    CK(cudaSetDevice(device));
-#endif
-    Slot &s = slot[si];
+// all stages for [b, e) into slot s (device buffers); the caller holds `mu`
+int nlzm_mf::compute(u64 b, u64 e, Slot &s) {
     s.begin = b; s.end = e; s.n_steps = 0;
     const u64 n_own = e - b;
+    const bool was_prepared = prepared && prep_b == b && prep_e == e;
+    prepared = false;
     for (int attempt = 0; attempt < 4; attempt++) {
         const u64 cap = n_own * tuple_cap_mult + (1u << 20);
         if (cap >= 0xFFFFFFF0ull) return fail(NLZM_MF_E_OVERFLOW, "candidate tuple capacity exceeds 2^32");
-        CKI(ensure(tk[0], cap * 8)); CKI(ensure(tk[1], cap * 8));
-        CKI(ensure(tv[0], cap * 4)); CKI(ensure(tv[1], cap * 4));
-        CK(cudaMemsetAsync(tcount.p, 0, 4, st));
-        cudaEvent_t e0, e1, e2, e3, e4;
-        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2); cudaEventCreate(&e3); cudaEventCreate(&e4);
+        const bool continue_prepared = was_prepared && attempt == 0;
+        if (!continue_prepared) {
+            CKI(ensure(tk[0], cap * 8)); CKI(ensure(tk[1], cap * 8));
+            CKI(ensure(tv[0], cap * 4)); CKI(ensure(tv[1], cap * 4));
+            CK(cudaMemsetAsync(tcount.p, 0, 4, st));
+            stats.ms_rank = stats.ms_levels = 0;
+        }
+        stats.ms_cross = 0;
+        stats.segments_queried = 0;
+        Ev e0, e1, e2, e3, e4;
         cudaEventRecord(e0, st);
-        stats.ms_rank = stats.ms_levels = 0;
         int r = 0;
         if (n_own > 0) {
-            if (r == 0 && (mask & NLZM_MF_BT4) && g.flen >= 4) r = stage_bt4(b, e);
+            if ((mask & NLZM_MF_BT4) && g.flen >= 4) {
+                // window behind the range: from retained segments when they cover it, else re-ranked with the range.
+                // A prepared range has no halo by construction: its segments must have been imported by now.
+                std::vector<Segment> behind;
+                const bool covered = covered_by_segments(b, behind);
+                if (was_prepared && !covered)
+                    return fail(NLZM_MF_E_STATE, "prepared range: the window behind it is not covered by imported segments");
+                const u64 halo_b = b > (u64)(g.W - 1) ? b - (g.W - 1) : 0;
+                if (!continue_prepared) r = stage_bt4_own(b, e, covered ? b : halo_b);
+                if (r == 0 && covered) r = stage_bt4_cross(b, e, behind);
+            }
             cudaEventRecord(e1, st);
             if (r == 0 && (mask & NLZM_MF_HT2)) { HtCfg c{1, 12, 2}; r = stage_ht(b, e, c); }
             if (r == 0 && (mask & NLZM_MF_HT3)) { HtCfg c{2, g.ht3_bits, 3}; r = stage_ht(b, e, c); }
@@ -541,46 +725,118 @@ int nlzm_mf::find_impl(u64 b, u64 e, int si, bool to_host) {
         cudaEventRecord(e4, st);
         cudaStreamSynchronize(st);
         if (r == 0) {
+            std::lock_guard<std::mutex> l(stats_mu);
             cudaEventElapsedTime(&stats.ms_ht, e1, e2);
             cudaEventElapsedTime(&stats.ms_rk, e2, e3);
             cudaEventElapsedTime(&stats.ms_merge, e3, e4);
             cudaEventElapsedTime(&stats.ms_total, e0, e4);
+            if (continue_prepared) stats.ms_total += stats.ms_prepare;
         }
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2); cudaEventDestroy(e3); cudaEventDestroy(e4);
         if (r == NLZM_MF_E_OVERFLOW && attempt < 3) {      // rare: dense candidates; grow and redo the range
             if (rk_overflowed) rk_overflowed = false; else tuple_cap_mult *= 2;
+            fresh.clear();
             continue;
         }
-        if (r) return r;
+        if (r) { fresh.clear(); return r; }
         break;
     }
-    stats.kernel_launches = g_launches.load();
-    stats.ms_d2h = 0;
-    if (g_prof.on) g_prof.resolve();
-    if (to_host) {
-        size_t ob = (n_own + 1) * 4, sb = (size_t)(s.n_steps ? s.n_steps : 1) * sizeof(Step);
-        if (ob > s.h_offsets_bytes) {
-            if (s.h_offsets) cudaFreeHost(s.h_offsets);
-            s.h_offsets = nullptr; s.h_offsets_bytes = 0;
-            CK(cudaMallocHost(&s.h_offsets, ob + (ob >> 3)));
-            s.h_offsets_bytes = ob + (ob >> 3);
-        }
-        if (sb > s.h_steps_bytes) {
-            if (s.h_steps) cudaFreeHost(s.h_steps);
-            s.h_steps = nullptr; s.h_steps_bytes = 0;
-            CK(cudaMallocHost(&s.h_steps, sb + (sb >> 3)));
-            s.h_steps_bytes = sb + (sb >> 3);
-        }
-        cudaEvent_t e0, e1;
-        cudaEventCreate(&e0); cudaEventCreate(&e1);
+    retain_fresh(e);
+    return 0;
+}
+
+// Stages S/T of [b, e) alone (no window behind it): what other engines need before they can import this
+// range's segments, and what nlzm_mf_find(b, e) then continues from.
+int nlzm_mf::prepare_impl(u64 b, u64 e) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!have_input) return fail(NLZM_MF_E_STATE, "prepare before set_input");
+    if (b > e || e > g.flen) return fail(NLZM_MF_E_ARG, "bad range");
+    if (e - b > (1ull << 28) || e - b > max_range) return fail(NLZM_MF_E_ARG, "range too large");
+    if (!(mask & NLZM_MF_BT4) || g.flen < 4 || e == b) { prepared = true; prep_b = b; prep_e = e; return 0; }
+#ifndef NLZM_EMU
+    CK(cudaSetDevice(device));
+#endif
+    prepared = false;
+    const u64 n_own = e - b;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        const u64 cap = n_own * tuple_cap_mult + (1u << 20);
+        if (cap >= 0xFFFFFFF0ull) return fail(NLZM_MF_E_OVERFLOW, "candidate tuple capacity exceeds 2^32");
+        CKI(ensure(tk[0], cap * 8)); CKI(ensure(tk[1], cap * 8));
+        CKI(ensure(tv[0], cap * 4)); CKI(ensure(tv[1], cap * 4));
+        CK(cudaMemsetAsync(tcount.p, 0, 4, st));
+        Ev e0, e1;
         cudaEventRecord(e0, st);
-        CK(cudaMemcpyAsync(s.h_offsets, s.d_offsets.p, ob, cudaMemcpyDeviceToHost, st));
-        if (s.n_steps) CK(cudaMemcpyAsync(s.h_steps, s.d_steps.p, s.n_steps * sizeof(Step), cudaMemcpyDeviceToHost, st));
-        cudaEventRecord(e1, st);
-        CK(cudaStreamSynchronize(st));
-        cudaEventElapsedTime(&stats.ms_d2h, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        int r = stage_bt4_own(b, e, b);
+        u32 nt = 0;
+        if (r == 0) {
+            cudaEventRecord(e1, st);
+            CK(cudaMemcpyAsync(&nt, tcount.p, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            cudaEventElapsedTime(&stats.ms_prepare, e0, e1);
+            if (nt > sink().cap) r = NLZM_MF_E_OVERFLOW;
+        }
+        if (r == NLZM_MF_E_OVERFLOW && attempt < 3) { tuple_cap_mult *= 2; fresh.clear(); continue; }
+        if (r) { fresh.clear(); return r == NLZM_MF_E_OVERFLOW ? fail(r, "candidate tuple buffer overflow") : r; }
+        break;
     }
+    if (g_prof.on) prof_resolve();
+    // the blocks are exported from the retained list; find(b, e) picks them up again as its own universe
+    for (const Segment &sg : fresh) segs.push_back(sg);
+    prepared = true; prep_b = b; prep_e = e;
+    return 0;
+}
+
+int nlzm_mf::find_impl(u64 b, u64 e, int si, bool to_host) {
+    std::unique_lock<std::mutex> lock(mu);
+    if (!have_input) return fail(NLZM_MF_E_STATE, "find before set_input");
+    if (si < 0 || si > 1) return fail(NLZM_MF_E_ARG, "slot must be 0 or 1");
+    if (b > e || e > g.flen) return fail(NLZM_MF_E_ARG, "bad range");
+    if (e - b > (1ull << 28)) return fail(NLZM_MF_E_ARG, "range larger than 2^28 positions: split it");
+    if (e - b > max_range) return fail(NLZM_MF_E_ARG, "range larger than config.max_range");
+#ifndef NLZM_EMU
+    CK(cudaSetDevice(device));
+#endif
+    Slot &s = slot[si];
+    CKI(compute(b, e, s));
+    const u64 n_own = e - b;
+    {
+        std::lock_guard<std::mutex> l(stats_mu);
+        stats.kernel_launches = g_launches.load();
+        stats.ms_d2h = 0;
+    }
+    if (g_prof.on) prof_resolve();
+    if (!to_host) return 0;
+    // Device -> host on the copy stream, outside the compute lock: the next range's kernels run while this
+    // range's records cross PCIe. The slot's device buffers stay untouched until its next find.
+    size_t ob = (n_own + 1) * 4, sb = (size_t)(s.n_steps ? s.n_steps : 1) * sizeof(Step);
+    if (ob > s.h_offsets_bytes) {
+        if (s.h_offsets) cudaFreeHost(s.h_offsets);
+        s.h_offsets = nullptr; s.h_offsets_bytes = 0;
+        CK(cudaMallocHost(&s.h_offsets, ob + (ob >> 3)));
+        s.h_offsets_bytes = ob + (ob >> 3);
+    }
+    if (sb > s.h_steps_bytes) {
+        if (s.h_steps) cudaFreeHost(s.h_steps);
+        s.h_steps = nullptr; s.h_steps_bytes = 0;
+        CK(cudaMallocHost(&s.h_steps, sb + (sb >> 3)));
+        s.h_steps_bytes = sb + (sb >> 3);
+    }
+    const u64 n_steps = s.n_steps;
+    void *d_off = s.d_offsets.p, *d_steps = s.d_steps.p;
+    lock.unlock();
+    Ev e0, e1;
+    cudaEventRecord(e0, st_copy);
+    cudaError_t ce = cudaMemcpyAsync(s.h_offsets, d_off, ob, cudaMemcpyDeviceToHost, st_copy);
+    if (ce == cudaSuccess && n_steps) ce = cudaMemcpyAsync(s.h_steps, d_steps, n_steps * sizeof(Step), cudaMemcpyDeviceToHost, st_copy);
+    cudaEventRecord(e1, st_copy);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st_copy);
+    if (ce != cudaSuccess) {
+        std::lock_guard<std::mutex> l(mu);
+        return fail((int)ce, std::string("device->host copy: ") + cudaGetErrorString(ce));
+    }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::lock_guard<std::mutex> l(stats_mu);
+    stats.ms_d2h = ms;
     return 0;
 }
 
@@ -627,7 +883,8 @@ int nlzm_mf_create(const nlzm_mf_config *cfg, nlzm_mf **out) {
     mf->mask = cfg->finder_mask ? cfg->finder_mask : (u32)NLZM_MF_ALL;
     mf->max_range = cfg->max_range ? cfg->max_range : cfg->file_len;
 #ifndef NLZM_EMU
-    if (cudaStreamCreateWithFlags(&mf->st, cudaStreamNonBlocking) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&mf->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&mf->st_copy, cudaStreamNonBlocking) != cudaSuccess) {
         g_create_error = "cudaStreamCreate failed";
         delete mf;
         return NLZM_MF_E_NODEVICE;
@@ -643,6 +900,14 @@ int nlzm_mf_create(const nlzm_mf_config *cfg, nlzm_mf **out) {
 
 void nlzm_mf_destroy(nlzm_mf *mf) {
     if (!mf) return;
+#ifndef NLZM_EMU
+    cudaSetDevice(mf->device);
+#endif
+    for (auto &s : mf->slot) if (s.worker.joinable()) s.worker.join();
+    mf->fresh.clear();
+    mf->segs.clear();                                  // buffers go back to the pool, which is freed below
+    for (auto &b : mf->pool) if (b.p) cudaFree(b.p);
+    mf->pool.clear();
     for (auto &s : mf->slot) {
         if (s.worker.joinable()) s.worker.join();
         mf->release(s.d_offsets); mf->release(s.d_steps);
@@ -657,6 +922,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
     for (DevBuf *b : all) mf->release(*b);
 #ifndef NLZM_EMU
     if (mf->st) cudaStreamDestroy(mf->st);
+    if (mf->st_copy) cudaStreamDestroy(mf->st_copy);
 #endif
     delete mf;
 }
@@ -675,6 +941,9 @@ static int set_input_common(nlzm_mf *mf, const void *src, uint64_t len, bool fro
         e = cudaMemcpyAsync(mf->x.p, src, len, from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, mf->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
     if (e != cudaSuccess) return mf->fail((int)e, std::string("set_input: ") + cudaGetErrorString(e));
+    mf->segs.clear();                                  // segments describe the previous bytes
+    mf->fresh.clear();
+    mf->prepared = false;
     mf->have_input = true;
     return 0;
 }
@@ -711,7 +980,13 @@ int nlzm_mf_submit(nlzm_mf *mf, uint64_t begin, uint64_t end, int slot) {
     if (s.pending) return mf->fail(NLZM_MF_E_STATE, "slot already has a pending submit");
     if (s.worker.joinable()) s.worker.join();
     try {
-        s.worker = std::thread([mf, begin, end, slot]() { mf->slot[slot].status = mf->find_impl(begin, end, slot, true); });
+        s.worker = std::thread([mf, begin, end, slot]() {
+            int r;
+            try { r = mf->find_impl(begin, end, slot, true); }
+            catch (const std::bad_alloc &) { r = NLZM_MF_E_NOMEM; }
+            catch (...) { r = NLZM_MF_E_STATE; }
+            mf->slot[slot].status = r;
+        });
     } catch (const std::exception &ex) {
         return mf->fail(NLZM_MF_E_NOMEM, std::string("cannot start the submit thread: ") + ex.what());
     }
@@ -729,8 +1004,111 @@ int nlzm_mf_fetch(nlzm_mf *mf, int slot, nlzm_mf_view *out) {
     return s.status;
 }
 
+int nlzm_mf_prepare(nlzm_mf *mf, uint64_t begin, uint64_t end) {
+    if (!mf) return NLZM_MF_E_ARG;
+    return mf->prepare_impl(begin, end);
+}
+
+int nlzm_mf_export_segments(nlzm_mf *mf, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out) {
+    if (!mf || !n_out) return NLZM_MF_E_ARG;
+    std::lock_guard<std::mutex> lock(mf->mu);
+#ifndef NLZM_EMU
+    cudaSetDevice(mf->device);
+#endif
+    uint32_t i = 0;
+    for (const Segment &sg : mf->segs) {
+        if (out && i < cap) {
+            nlzm_mf_segment &d = out[i];
+            memset(&d, 0, sizeof d);
+            d.pos_begin = sg.pos_b;
+            d.pos_end = sg.pos_e;
+            d.origin = sg.u0;
+            d.n_elems = sg.n_elems;
+            d.elems_offset_bytes = sg.elem_off * sizeof(Elem);
+            d.elems_bytes = (u64)sg.n_elems * sizeof(Elem);
+            d.ptrs_offset_bytes = (sg.pos_b - sg.ptr_pos0) * sizeof(PtrEntry);
+            d.ptrs_bytes = (sg.pos_e - sg.pos_b) * sizeof(PtrEntry);
+            d.elems_alloc = sg.bufs->el.p;
+            d.ptrs_alloc = sg.bufs->ptr.p;
+            d.device = mf->device;
+#ifndef NLZM_EMU
+            cudaIpcMemHandle_t h;
+            if (cudaIpcGetMemHandle(&h, sg.bufs->el.p) == cudaSuccess) { memcpy(d.ipc_elems, &h, sizeof h); d.flags |= 1u; }
+            if (cudaIpcGetMemHandle(&h, sg.bufs->ptr.p) == cudaSuccess) { memcpy(d.ipc_ptrs, &h, sizeof h); d.flags |= 2u; }
+            cudaGetLastError();
+#endif
+        }
+        ++i;
+    }
+    *n_out = i;
+    return 0;
+}
+
+int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
+    if (!mf || !d || d->pos_end <= d->pos_begin || d->pos_begin < d->origin) return NLZM_MF_E_ARG;
+    if (d->elems_bytes != d->n_elems * sizeof(Elem) || d->ptrs_bytes != (d->pos_end - d->pos_begin) * sizeof(PtrEntry))
+        return mf->fail(NLZM_MF_E_ARG, "segment descriptor sizes do not match this library's element layout");
+    std::lock_guard<std::mutex> lock(mf->mu);
+    if (d->pos_end > mf->g.flen) return mf->fail(NLZM_MF_E_ARG, "segment lies outside this engine's input");
+#ifndef NLZM_EMU
+    cudaSetDevice(mf->device);
+#endif
+    auto bufs = std::make_shared<SegBufs>();
+    bufs->owner = mf;
+    int r = mf->ensure_pooled(bufs->el, (size_t)d->elems_bytes);
+    if (r == 0) r = mf->ensure_pooled(bufs->ptr, (size_t)d->ptrs_bytes);
+    if (r) return r;
+    const u8 *src_el = (const u8 *)d->elems_alloc, *src_ptr = (const u8 *)d->ptrs_alloc;
+#ifndef NLZM_EMU
+    void *open_el = nullptr, *open_ptr = nullptr;
+    if (via_ipc) {
+        if ((d->flags & 3u) != 3u) return mf->fail(NLZM_MF_E_ARG, "segment descriptor carries no IPC handles");
+        cudaIpcMemHandle_t h;
+        memcpy(&h, d->ipc_elems, sizeof h);
+        cudaError_t e = cudaIpcOpenMemHandle(&open_el, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e == cudaSuccess) { memcpy(&h, d->ipc_ptrs, sizeof h); e = cudaIpcOpenMemHandle(&open_ptr, h, cudaIpcMemLazyEnablePeerAccess); }
+        if (e != cudaSuccess) {
+            if (open_el) cudaIpcCloseMemHandle(open_el);
+            return mf->fail((int)e, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        }
+        src_el = (const u8 *)open_el;
+        src_ptr = (const u8 *)open_ptr;
+    }
+    cudaError_t e = cudaMemcpyPeerAsync(bufs->el.p, mf->device, src_el + d->elems_offset_bytes, via_ipc ? mf->device : d->device, (size_t)d->elems_bytes, mf->st);
+    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(bufs->ptr.p, mf->device, src_ptr + d->ptrs_offset_bytes, via_ipc ? mf->device : d->device, (size_t)d->ptrs_bytes, mf->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
+    if (open_el) cudaIpcCloseMemHandle(open_el);
+    if (open_ptr) cudaIpcCloseMemHandle(open_ptr);
+    if (e != cudaSuccess) return mf->fail((int)e, std::string("segment copy: ") + cudaGetErrorString(e));
+#else
+    (void)via_ipc;
+    memcpy(bufs->el.p, src_el + d->elems_offset_bytes, (size_t)d->elems_bytes);
+    memcpy(bufs->ptr.p, src_ptr + d->ptrs_offset_bytes, (size_t)d->ptrs_bytes);
+#endif
+    Segment sg;
+    sg.bufs = bufs;
+    sg.u0 = d->origin;
+    sg.elem_off = 0;
+    sg.n_elems = (u32)d->n_elems;
+    sg.ptr_pos0 = d->pos_begin;
+    sg.pos_b = d->pos_begin;
+    sg.pos_e = d->pos_end;
+    for (const Segment &o : mf->segs) if (o.pos_b == sg.pos_b && o.pos_e == sg.pos_e) return 0;   // already there
+    mf->segs.push_back(sg);
+    return 0;
+}
+
+int nlzm_mf_drop_segments(nlzm_mf *mf) {
+    if (!mf) return NLZM_MF_E_ARG;
+    std::lock_guard<std::mutex> lock(mf->mu);
+    mf->segs.clear();
+    mf->fresh.clear();
+    mf->prepared = false;
+    return 0;
+}
+
 int nlzm_mf_profile(int enable) {
-    g_prof.on = enable != 0;
+    g_prof.on.store(enable != 0);
     if (!enable) {
         std::lock_guard<std::mutex> l(g_prof.mu);
         g_prof.acc.clear();
@@ -760,6 +1138,8 @@ int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value) {
     std::lock_guard<std::mutex> lock(mf->mu);
     const std::string k(key);
     if (k == "ht_margin") { mf->ht_margin = value; return 0; }
+    if (k == "retain") { mf->retain = value != 0; if (!mf->retain) mf->segs.clear(); return 0; }
+    if (k == "max_segments") { mf->max_segments = (u32)value; return 0; }
     if (k == "ht_coarse_log") {
         if (value < NLZM_HT_TILE_LOG && value < 10) return mf->fail(NLZM_MF_E_ARG, "ht_coarse_log too small");
         if (value > 30) return mf->fail(NLZM_MF_E_ARG, "ht_coarse_log too large");
@@ -771,7 +1151,10 @@ int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value) {
 
 int nlzm_mf_get_stats(const nlzm_mf *mf, nlzm_mf_stats *out) {
     if (!mf || !out) return NLZM_MF_E_ARG;
-    *out = mf->stats;
+    {
+        std::lock_guard<std::mutex> l(const_cast<nlzm_mf *>(mf)->stats_mu);
+        *out = mf->stats;
+    }
     out->kernel_launches = g_launches.load();
     return 0;
 }

@@ -223,11 +223,9 @@ __global__ void __launch_bounds__(32) k_ht_prev(const HtTableParams p) {
 }
 static inline int launch_ht_prev(const HtTableParams &p, u64 grid, size_t smem, cudaStream_t st) {
     if (grid == 0) return 0;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_ht_prev, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
+    if (smem > 48 * 1024) {
+        int e = nlzm_smem_opt_in((const void *)k_ht_prev, smem);
+        if (e) return e;
     }
     nlzm_launch_begin("k_ht_prev", st);
     k_ht_prev<<<(unsigned)grid, 32, smem, st>>>(p);

@@ -40,11 +40,9 @@ typedef int64_t i64;
     }                                                                                   \
     static inline int launch_##name(const ParamsT &p, u64 grid, size_t smem, cudaStream_t st) { \
         if (grid == 0) return 0;                                                        \
-        static size_t configured = 0;                                                   \
-        if (smem > 48 * 1024 && smem > configured) {                                    \
-            cudaError_t e = cudaFuncSetAttribute(k_##name, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            if (e != cudaSuccess) return (int)e;                                        \
-            configured = smem;                                                          \
+        if (smem > 48 * 1024) {                                                         \
+            int e = nlzm_smem_opt_in((const void *)k_##name, smem);                     \
+            if (e) return e;                                                            \
         }                                                                               \
         nlzm_launch_begin("k_" #name, st);                                              \
         k_##name<<<(unsigned)grid, NT, smem, st>>>(p);                                  \
@@ -52,6 +50,32 @@ typedef int64_t i64;
         return (int)cudaGetLastError();                                                 \
     }
 #define NLZM_CTA_SYNC() __syncthreads()
+// Opt-in to more than 48 KiB of dynamic shared memory. The attribute belongs to the (kernel, device) pair, and one
+// process may drive engines on several devices, so the size already granted is remembered per device.
+#include <atomic>
+static inline int nlzm_smem_opt_in(const void *kernel, size_t smem) {
+    struct Granted { std::atomic<const void *> fn{nullptr}; std::atomic<size_t> bytes[64]; };
+    static Granted table[32];                                   // a handful of kernels need the opt-in
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = -1;
+    Granted *g = nullptr;
+    for (auto &t : table) {
+        const void *cur = t.fn.load(std::memory_order_acquire);
+        if (cur == kernel) { g = &t; break; }
+        if (cur == nullptr) {
+            const void *expect = nullptr;
+            if (t.fn.compare_exchange_strong(expect, kernel, std::memory_order_acq_rel) || expect == kernel) { g = &t; break; }
+        }
+    }
+    if (g && dev >= 0 && g->bytes[dev].load(std::memory_order_acquire) >= smem) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (g && dev >= 0) {                                        // racing threads set the same attribute: benign
+        size_t old = g->bytes[dev].load(std::memory_order_relaxed);
+        while (old < smem && !g->bytes[dev].compare_exchange_weak(old, smem, std::memory_order_release)) {}
+    }
+    return 0;
+}
 DEV u32 nlzm_atomic_add(u32 *p, u32 v) { return atomicAdd(p, v); }
 DEV u64 nlzm_atomic_add64(unsigned long long *p, u64 v) { return atomicAdd(p, (unsigned long long)v); }
 DEV u32 nlzm_atomic_max(u32 *p, u32 v) { return atomicMax(p, v); }

@@ -97,6 +97,27 @@ class MatchFinders:
         self._check(self._L.nlzm_mf_fetch(self._h, slot, C.byref(v)), "fetch")
         return self._view_to_numpy(v, copy)
 
+    # -- position sharding across engines / GPUs (include/nlzm_mf.h: segments) ---------------------------
+    def prepare(self, begin: int, end: int) -> None:
+        """rank + merge [begin, end) alone; other engines can then import its segments, find() continues from here"""
+        self._check(self._L.nlzm_mf_prepare(self._h, begin, end), "prepare")
+
+    def export_segments(self) -> list:
+        n = C.c_uint32(0)
+        self._check(self._L.nlzm_mf_export_segments(self._h, None, 0, C.byref(n)), "export_segments")
+        arr = (_lib.SegmentDesc * max(n.value, 1))()
+        self._check(self._L.nlzm_mf_export_segments(self._h, arr, n.value, C.byref(n)), "export_segments")
+        return [arr[i] for i in range(n.value)]
+
+    def import_segment(self, desc, via_ipc: bool = False) -> None:
+        """desc: a SegmentDesc from export_segments() of another engine, or its bytes (from another process)"""
+        if isinstance(desc, (bytes, bytearray)):
+            desc = _lib.SegmentDesc.from_buffer_copy(desc)
+        self._check(self._L.nlzm_mf_import_segment(self._h, C.byref(desc), int(via_ipc)), "import_segment")
+
+    def drop_segments(self) -> None:
+        self._check(self._L.nlzm_mf_drop_segments(self._h), "drop_segments")
+
     def set_option(self, key: str, value: int) -> None:
         """tuning / test knobs, see nlzm_mf_set_option in include/nlzm_mf.h"""
         self._check(self._L.nlzm_mf_set_option(self._h, key.encode(), value), "set_option")

@@ -106,3 +106,86 @@ def test_error_paths(emu_lib):
     with pytest.raises(MatchFinderError):
         mf.fetch(0)
     mf.Release()
+
+
+def _blocks(mf, cuts):
+    offs, ds, ls, base, used = [np.zeros(1, np.uint64)], [], [], 0, []
+    for i, (b, e) in enumerate(zip(cuts[:-1], cuts[1:])):
+        off, st = mf.FindAndUpdate(b, e, slot=i & 1)
+        used.append(int(mf.stats().segments_queried))
+        offs.append(off[1:].astype(np.uint64) + base)
+        base += int(off[-1])
+        ds.append(st["dist"].copy())
+        ls.append(st["len"].copy())
+    return (np.concatenate(offs), np.concatenate(ds), np.concatenate(ls)), used
+
+
+@pytest.mark.parametrize("kind,hb", [("text", 15), ("longrange", 15), ("mixed", 16), ("zeros", 15)])
+def test_emu_retained_segments(emu_lib, orc, kind, hb):
+    """consecutive ranges query the retained segments of the ranges before them instead of re-ranking the
+    window; the result equals the oracle (and the from-scratch path, option retain=0)"""
+    from nlzm_b200 import synth
+    from nlzm_b200.matchfinder import MatchFinders
+    n = 150_000 if kind != "zeros" else 80_000
+    x = synth.make(kind, n)
+    ref = orc.find(x, hb, orc.F_ALL)
+    for cuts in ([0, 40_000, 47_000, n - 30_001, n], [0, 9_000, 18_000, 27_000, 36_000, 45_000, 54_000, n - 9_000, n]):
+        with MatchFinders(emu_lib) as mf:
+            mf.Init(hb, x)
+            got, used = _blocks(mf, cuts)
+            assert orc.csr_equal(ref, got), (cuts, orc.first_diff(ref, got))
+            assert used[0] == 0 and all(u > 0 for u in used[1:]), used
+        with MatchFinders(emu_lib) as mf:
+            mf.Init(hb, x)
+            mf.set_option("retain", 0)
+            got, used = _blocks(mf, cuts)
+            assert orc.csr_equal(ref, got) and not any(used)
+
+
+def test_emu_retained_falls_back_when_not_consecutive(emu_lib, orc):
+    from nlzm_b200 import synth
+    from nlzm_b200.matchfinder import MatchFinders
+    x = synth.text(120_000, 5)
+    ref = orc.find(x, 15, orc.F_ALL)
+    with MatchFinders(emu_lib) as mf:
+        mf.Init(15, x)
+        mf.FindAndUpdate(0, 30_000)
+        off, st = mf.FindAndUpdate(70_000, 120_000, slot=1)          # gap: window re-ranked with the range
+        assert mf.stats().segments_queried == 0
+        lo, hi = int(ref[0][70_000]), int(ref[0][120_000])
+        assert np.array_equal(st["dist"], ref[1][lo:hi]) and np.array_equal(st["len"], ref[2][lo:hi])
+        assert np.array_equal(off.astype(np.uint64), ref[0][70_000:] - ref[0][70_000])
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_emu_sharded_engines_import_segments(emu_lib, orc, world):
+    """position sharding: every engine prepares its own range, imports the segments behind it from the
+    engines that own them, then finds; the concatenation equals the oracle"""
+    from nlzm_b200 import synth, sharding
+    from nlzm_b200.matchfinder import MatchFinders
+    x = synth.longrange(160_000, 9)
+    hb = 16                                               # W = 65536: a shard of 32000 needs two or three neighbours
+    ref = orc.find(x, hb, orc.F_ALL)
+    W = 1 << hb
+    engines = [MatchFinders(emu_lib) for _ in range(world)]
+    ranges = [sharding.shard_range(x.size, r, world) for r in range(world)]
+    try:
+        for mf, (b, e) in zip(engines, ranges):
+            mf.Init(hb, x)
+            mf.prepare(b, e)
+        descs = [mf.export_segments() for mf in engines]
+        parts = []
+        for r, (mf, (b, e)) in enumerate(zip(engines, ranges)):
+            for q in range(r):
+                for d in descs[q]:
+                    if d.pos_end > max(0, b - (W - 1)):
+                        mf.import_segment(bytes(d))
+            off, st = mf.FindAndUpdate(b, e)
+            if r > 0:
+                assert mf.stats().segments_queried > 0
+            parts.append((b, e, off, st))
+        got = sharding.concat_views(parts)
+        assert orc.csr_equal(ref, got), orc.first_diff(ref, got)
+    finally:
+        for mf in engines:
+            mf.Release()

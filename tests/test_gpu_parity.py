@@ -114,7 +114,7 @@ def test_submit_fetch_pipeline(cuda_lib, orc):
 
 def test_properties_at_scale(cuda_lib):
     """32 MB text, -window:24: every step is a true, maximal match; steps strictly increase; distances
-    stay inside the window; a sample of positions is checked against a brute-force window scan."""
+    stay inside the window (validity only: completeness is tests/test_gpu_scale.py's job)."""
     from nlzm_b200 import synth
     x = synth.text(32_000_000, 51)
     off, st = _run(cuda_lib, x, 24)[0], None
@@ -138,8 +138,8 @@ def test_properties_at_scale(cuda_lib):
     for j in rng.integers(0, pos.size, 20000):
         a, d, l = int(pos[j]), int(dist[j]), int(ln[j])
         assert np.array_equal(x[a:a + l], x[a - d:a - d + l])
-        end = a + l
-        assert l == 264 or end >= n or x[end] != x[end - d] or True   # HT/RK steps need not be maximal
+    # completeness (no candidate missing, none nearer) is checked against a brute-force scan of the whole window in
+    # tests/test_gpu_scale.py::test_brute_force_window_scan_sampled and bit-exactly at full size in the digest tests
 
 
 def _check_properties(x, off, st, begin, W):
