@@ -144,7 +144,10 @@ typedef struct {
 } nlzm_mf_segment;
 int nlzm_mf_prepare(nlzm_mf *mf, uint64_t begin, uint64_t end);
 int nlzm_mf_export_segments(nlzm_mf *mf, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out);
-int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *seg, int via_ipc);
+/* via: 0 = elems_alloc / ptrs_alloc are device pointers of this process (peer copy), 1 = open the IPC handles,
+ *      2 = elems_alloc / ptrs_alloc are HOST copies of the two slices made with nlzm_mf_read_segment */
+int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *seg, int via);
+int nlzm_mf_read_segment(nlzm_mf *mf, uint32_t index, void *elems_host, void *ptrs_host);
 int nlzm_mf_drop_segments(nlzm_mf *mf);
 
 /* Tuning / test knobs (no reference counterpart; results never depend on them):

@@ -16,6 +16,7 @@
 #include "merge_steps.cuh"
 
 #include <atomic>
+#include <condition_variable>
 #include <map>
 #include <mutex>
 #include <memory>
@@ -139,6 +140,7 @@ struct Segment {
     }
 };
 
+struct Turn;
 struct nlzm_mf {
     Geom g;
     int device = 0;
@@ -169,11 +171,22 @@ struct nlzm_mf {
     u64 fresh_u0 = 0;
     bool prepared = false;                 // nlzm_mf_prepare ran stages S/T for [prep_b, prep_e): find continues from there
     u64 prep_b = 0, prep_e = 0;
+    std::vector<Segment> prep_fresh;       // ... with these blocks and these candidate tuples (other ranges may be
+    DevBuf prep_tk, prep_tv;               //     found in between: the first range of a shard finishes last)
+    u32 prep_nt = 0;
+    float prep_ms_rank = 0, prep_ms_levels = 0, prep_ms = 0;
     std::vector<DevBuf> pool;              // level-array / pointer buffers waiting to be reused
     std::mutex pool_mu;
 
     Slot slot[2];
-    std::mutex mu;                         // one find computes at a time
+    // One call computes at a time, in the order the calls were MADE: a submit takes its turn in the caller's thread,
+    // so the set_input / prepare / find that follow it cannot overtake the worker thread it spawned.
+    std::mutex turn_mu;
+    std::condition_variable turn_cv;
+    u64 turn_next = 0, turn_serving = 0;
+    u64 take_turn() { std::lock_guard<std::mutex> l(turn_mu); return turn_next++; }
+    void wait_turn(u64 t) { std::unique_lock<std::mutex> l(turn_mu); turn_cv.wait(l, [&] { return turn_serving == t; }); }
+    void end_turn() { { std::lock_guard<std::mutex> l(turn_mu); ++turn_serving; } turn_cv.notify_all(); }
     std::mutex stats_mu;
     std::string err;
     nlzm_mf_stats stats{};
@@ -255,12 +268,23 @@ struct nlzm_mf {
     int stage_bt4_own(u64 own_b, u64 own_e, u64 u0);
     int stage_bt4_cross(u64 own_b, u64 own_e, const std::vector<Segment> &behind);
     void retain_fresh(u64 own_e);
+    void add_segments(const std::vector<Segment> &v);
     int stage_ht(u64 own_b, u64 own_e, const HtCfg &c);
     int stage_rk(u64 own_b, u64 own_e);
     int stage_merge(u64 own_b, u64 own_e, Slot &s);
     int compute(u64 b, u64 e, Slot &s);
-    int find_impl(u64 b, u64 e, int slot, bool to_host);
+    int find_impl(u64 b, u64 e, int slot, bool to_host, u64 ticket);
     int prepare_impl(u64 b, u64 e);
+};
+
+// scope of one call's turn on the engine
+struct Turn {
+    nlzm_mf *mf;
+    bool held = true;
+    static const u64 NONE = ~0ull;
+    Turn(nlzm_mf *m, u64 ticket = NONE) : mf(m) { mf->wait_turn(ticket == NONE ? mf->take_turn() : ticket); }
+    void release() { if (held) { held = false; mf->end_turn(); } }
+    ~Turn() { release(); }
 };
 
 SegBufs::~SegBufs() {
@@ -493,18 +517,24 @@ int nlzm_mf::stage_bt4_cross(u64 own_b, u64 own_e, const std::vector<Segment> &b
     return 0;
 }
 
+// new blocks replace whatever the list holds for the same positions
+void nlzm_mf::add_segments(const std::vector<Segment> &v) {
+    if (v.empty()) return;
+    const u64 lo = v.front().pos_b, hi = v.back().pos_e;
+    std::vector<Segment> kept;
+    for (Segment &o : segs) if (o.pos_e <= lo || o.pos_b >= hi) kept.push_back(o);
+    for (const Segment &sg : v) kept.push_back(sg);
+    segs.swap(kept);
+}
+
 // after a find: its blocks join the retained list; whatever a range starting at own_e could not reach goes
 void nlzm_mf::retain_fresh(u64 own_e) {
-    if (!retain) { fresh.clear(); segs.clear(); return; }
-    for (Segment &sg : fresh) {
-        bool dup = false;
-        for (const Segment &o : segs) if (o.pos_b == sg.pos_b && o.pos_e == sg.pos_e) dup = true;
-        if (!dup) segs.push_back(sg);
-    }
+    if (!retain) { fresh.clear(); segs.clear(); stats.segments_retained = 0; return; }
+    add_segments(fresh);
     fresh.clear();
     const u64 keep_from = own_e > (u64)(g.W - 1) ? own_e - (g.W - 1) : 0;
     std::vector<Segment> kept;
-    for (Segment &sg : segs) if (sg.pos_e > keep_from && sg.pos_e <= own_e) kept.push_back(sg);
+    for (Segment &sg : segs) if (sg.pos_e > keep_from && (sg.pos_e <= own_e || (prepared && sg.pos_b >= prep_b && sg.pos_e <= prep_e))) kept.push_back(sg);
     segs.swap(kept);
     stats.segments_retained = (u32)segs.size();
 }
@@ -684,16 +714,28 @@ int nlzm_mf::compute(u64 b, u64 e, Slot &s) {
     s.begin = b; s.end = e; s.n_steps = 0;
     const u64 n_own = e - b;
     const bool was_prepared = prepared && prep_b == b && prep_e == e;
-    prepared = false;
+    if (was_prepared) prepared = false;
     for (int attempt = 0; attempt < 4; attempt++) {
         const u64 cap = n_own * tuple_cap_mult + (1u << 20);
         if (cap >= 0xFFFFFFF0ull) return fail(NLZM_MF_E_OVERFLOW, "candidate tuple capacity exceeds 2^32");
         const bool continue_prepared = was_prepared && attempt == 0;
+        CKI(ensure(tk[0], cap * 8)); CKI(ensure(tk[1], cap * 8));
+        CKI(ensure(tv[0], cap * 4)); CKI(ensure(tv[1], cap * 4));
         if (!continue_prepared) {
-            CKI(ensure(tk[0], cap * 8)); CKI(ensure(tk[1], cap * 8));
-            CKI(ensure(tv[0], cap * 4)); CKI(ensure(tv[1], cap * 4));
             CK(cudaMemsetAsync(tcount.p, 0, 4, st));
             stats.ms_rank = stats.ms_levels = 0;
+        } else {
+            // stages S/T of this range ran in nlzm_mf_prepare: take its blocks and candidate tuples back
+            fresh = prep_fresh;
+            prep_fresh.clear();
+            fresh_u0 = b;
+            if (prep_nt) {
+                CK(cudaMemcpyAsync(tk[0].p, prep_tk.p, (size_t)prep_nt * 8, cudaMemcpyDeviceToDevice, st));
+                CK(cudaMemcpyAsync(tv[0].p, prep_tv.p, (size_t)prep_nt * 4, cudaMemcpyDeviceToDevice, st));
+            }
+            CK(cudaMemcpyAsync(tcount.p, &prep_nt, 4, cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            stats.ms_rank = prep_ms_rank; stats.ms_levels = prep_ms_levels;
         }
         stats.ms_cross = 0;
         stats.segments_queried = 0;
@@ -730,7 +772,7 @@ int nlzm_mf::compute(u64 b, u64 e, Slot &s) {
             cudaEventElapsedTime(&stats.ms_rk, e2, e3);
             cudaEventElapsedTime(&stats.ms_merge, e3, e4);
             cudaEventElapsedTime(&stats.ms_total, e0, e4);
-            if (continue_prepared) stats.ms_total += stats.ms_prepare;
+            if (continue_prepared) stats.ms_total += prep_ms;
         }
         if (r == NLZM_MF_E_OVERFLOW && attempt < 3) {      // rare: dense candidates; grow and redo the range
             if (rk_overflowed) rk_overflowed = false; else tuple_cap_mult *= 2;
@@ -747,11 +789,11 @@ int nlzm_mf::compute(u64 b, u64 e, Slot &s) {
 // Stages S/T of [b, e) alone (no window behind it): what other engines need before they can import this
 // range's segments, and what nlzm_mf_find(b, e) then continues from.
 int nlzm_mf::prepare_impl(u64 b, u64 e) {
-    std::lock_guard<std::mutex> lock(mu);
+    Turn turn(this);
     if (!have_input) return fail(NLZM_MF_E_STATE, "prepare before set_input");
     if (b > e || e > g.flen) return fail(NLZM_MF_E_ARG, "bad range");
     if (e - b > (1ull << 28) || e - b > max_range) return fail(NLZM_MF_E_ARG, "range too large");
-    if (!(mask & NLZM_MF_BT4) || g.flen < 4 || e == b) { prepared = true; prep_b = b; prep_e = e; return 0; }
+    if (!(mask & NLZM_MF_BT4) || g.flen < 4 || e == b) { prepared = true; prep_b = b; prep_e = e; prep_nt = 0; prep_fresh.clear(); prep_ms = prep_ms_rank = prep_ms_levels = 0; return 0; }
 #ifndef NLZM_EMU
     CK(cudaSetDevice(device));
 #endif
@@ -780,13 +822,26 @@ int nlzm_mf::prepare_impl(u64 b, u64 e) {
     }
     if (g_prof.on) prof_resolve();
     // the blocks are exported from the retained list; find(b, e) picks them up again as its own universe
-    for (const Segment &sg : fresh) segs.push_back(sg);
+    u32 nt = 0;
+    CK(cudaMemcpyAsync(&nt, tcount.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CKI(ensure(prep_tk, (size_t)(nt ? nt : 1) * 8)); CKI(ensure(prep_tv, (size_t)(nt ? nt : 1) * 4));
+    if (nt) {
+        CK(cudaMemcpyAsync(prep_tk.p, tk[0].p, (size_t)nt * 8, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(prep_tv.p, tv[0].p, (size_t)nt * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    prep_nt = nt;
+    prep_fresh = fresh;
+    prep_ms_rank = stats.ms_rank; prep_ms_levels = stats.ms_levels; prep_ms = stats.ms_prepare;
+    add_segments(fresh);
+    fresh.clear();
     prepared = true; prep_b = b; prep_e = e;
     return 0;
 }
 
-int nlzm_mf::find_impl(u64 b, u64 e, int si, bool to_host) {
-    std::unique_lock<std::mutex> lock(mu);
+int nlzm_mf::find_impl(u64 b, u64 e, int si, bool to_host, u64 ticket) {
+    Turn turn(this, ticket);
     if (!have_input) return fail(NLZM_MF_E_STATE, "find before set_input");
     if (si < 0 || si > 1) return fail(NLZM_MF_E_ARG, "slot must be 0 or 1");
     if (b > e || e > g.flen) return fail(NLZM_MF_E_ARG, "bad range");
@@ -822,17 +877,14 @@ int nlzm_mf::find_impl(u64 b, u64 e, int si, bool to_host) {
     }
     const u64 n_steps = s.n_steps;
     void *d_off = s.d_offsets.p, *d_steps = s.d_steps.p;
-    lock.unlock();
+    turn.release();
     Ev e0, e1;
     cudaEventRecord(e0, st_copy);
     cudaError_t ce = cudaMemcpyAsync(s.h_offsets, d_off, ob, cudaMemcpyDeviceToHost, st_copy);
     if (ce == cudaSuccess && n_steps) ce = cudaMemcpyAsync(s.h_steps, d_steps, n_steps * sizeof(Step), cudaMemcpyDeviceToHost, st_copy);
     cudaEventRecord(e1, st_copy);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st_copy);
-    if (ce != cudaSuccess) {
-        std::lock_guard<std::mutex> l(mu);
-        return fail((int)ce, std::string("device->host copy: ") + cudaGetErrorString(ce));
-    }
+    if (ce != cudaSuccess) return fail((int)ce, std::string("device->host copy: ") + cudaGetErrorString(ce));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     std::lock_guard<std::mutex> l(stats_mu);
@@ -905,6 +957,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
 #endif
     for (auto &s : mf->slot) if (s.worker.joinable()) s.worker.join();
     mf->fresh.clear();
+    mf->prep_fresh.clear();
     mf->segs.clear();                                  // buffers go back to the pool, which is freed below
     for (auto &b : mf->pool) if (b.p) cudaFree(b.p);
     mf->pool.clear();
@@ -918,7 +971,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
                      &mf->aux1, &mf->tk[0], &mf->tk[1], &mf->tv[0], &mf->tv[1], &mf->tcount, &mf->keep, &mf->out_idx,
                      &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->ht_tab, &mf->ht_gmax, &mf->ht_coarse, &mf->ht_cfirst, &mf->ht_clast, &mf->ht_ccount, &mf->ht_ps, &mf->ht_pl, &mf->ht_pr, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
                      &mf->sl_v[0], &mf->sl_v[1], &mf->sl_cnt, &mf->sl_off, &mf->hit_k[0], &mf->hit_k[1], &mf->hit_v[0],
-                     &mf->hit_v[1], &mf->hit_len, &mf->iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf};
+                     &mf->hit_v[1], &mf->hit_len, &mf->iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf, &mf->prep_tk, &mf->prep_tv};
     for (DevBuf *b : all) mf->release(*b);
 #ifndef NLZM_EMU
     if (mf->st) cudaStreamDestroy(mf->st);
@@ -932,7 +985,7 @@ const char *nlzm_mf_last_error(const nlzm_mf *mf) { return mf ? mf->err.c_str() 
 static int set_input_common(nlzm_mf *mf, const void *src, uint64_t len, bool from_device) {
     if (!mf || (!src && len)) return NLZM_MF_E_ARG;
     if (len != mf->g.flen) return mf->fail(NLZM_MF_E_ARG, "set_input length differs from config.file_len");
-    std::lock_guard<std::mutex> lock(mf->mu);
+    Turn turn(mf);
 #ifndef NLZM_EMU
     cudaSetDevice(mf->device);
 #endif
@@ -943,6 +996,7 @@ static int set_input_common(nlzm_mf *mf, const void *src, uint64_t len, bool fro
     if (e != cudaSuccess) return mf->fail((int)e, std::string("set_input: ") + cudaGetErrorString(e));
     mf->segs.clear();                                  // segments describe the previous bytes
     mf->fresh.clear();
+    mf->prep_fresh.clear();
     mf->prepared = false;
     mf->have_input = true;
     return 0;
@@ -962,14 +1016,14 @@ static void fill_view(nlzm_mf *mf, int slot, bool host, nlzm_mf_view *out) {
 
 int nlzm_mf_find(nlzm_mf *mf, uint64_t begin, uint64_t end, int slot, nlzm_mf_view *out) {
     if (!mf || !out) return NLZM_MF_E_ARG;
-    int r = mf->find_impl(begin, end, slot, true);
+    int r = mf->find_impl(begin, end, slot, true, Turn::NONE);
     if (r == 0) fill_view(mf, slot, true, out);
     return r;
 }
 
 int nlzm_mf_find_device(nlzm_mf *mf, uint64_t begin, uint64_t end, int slot, nlzm_mf_view *out) {
     if (!mf || !out) return NLZM_MF_E_ARG;
-    int r = mf->find_impl(begin, end, slot, false);
+    int r = mf->find_impl(begin, end, slot, false, Turn::NONE);
     if (r == 0) fill_view(mf, slot, false, out);
     return r;
 }
@@ -979,15 +1033,18 @@ int nlzm_mf_submit(nlzm_mf *mf, uint64_t begin, uint64_t end, int slot) {
     Slot &s = mf->slot[slot];
     if (s.pending) return mf->fail(NLZM_MF_E_STATE, "slot already has a pending submit");
     if (s.worker.joinable()) s.worker.join();
+    const u64 ticket = mf->take_turn();            // the worker computes in the order of the calls, not of the threads
     try {
-        s.worker = std::thread([mf, begin, end, slot]() {
+        s.worker = std::thread([mf, begin, end, slot, ticket]() {
             int r;
-            try { r = mf->find_impl(begin, end, slot, true); }
+            try { r = mf->find_impl(begin, end, slot, true, ticket); }
             catch (const std::bad_alloc &) { r = NLZM_MF_E_NOMEM; }
             catch (...) { r = NLZM_MF_E_STATE; }
             mf->slot[slot].status = r;
         });
     } catch (const std::exception &ex) {
+        mf->wait_turn(ticket);
+        mf->end_turn();
         return mf->fail(NLZM_MF_E_NOMEM, std::string("cannot start the submit thread: ") + ex.what());
     }
     s.pending = true;
@@ -1011,7 +1068,7 @@ int nlzm_mf_prepare(nlzm_mf *mf, uint64_t begin, uint64_t end) {
 
 int nlzm_mf_export_segments(nlzm_mf *mf, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out) {
     if (!mf || !n_out) return NLZM_MF_E_ARG;
-    std::lock_guard<std::mutex> lock(mf->mu);
+    Turn turn(mf);
 #ifndef NLZM_EMU
     cudaSetDevice(mf->device);
 #endif
@@ -1048,7 +1105,7 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
     if (!mf || !d || d->pos_end <= d->pos_begin || d->pos_begin < d->origin) return NLZM_MF_E_ARG;
     if (d->elems_bytes != d->n_elems * sizeof(Elem) || d->ptrs_bytes != (d->pos_end - d->pos_begin) * sizeof(PtrEntry))
         return mf->fail(NLZM_MF_E_ARG, "segment descriptor sizes do not match this library's element layout");
-    std::lock_guard<std::mutex> lock(mf->mu);
+    Turn turn(mf);
     if (d->pos_end > mf->g.flen) return mf->fail(NLZM_MF_E_ARG, "segment lies outside this engine's input");
 #ifndef NLZM_EMU
     cudaSetDevice(mf->device);
@@ -1059,6 +1116,13 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
     if (r == 0) r = mf->ensure_pooled(bufs->ptr, (size_t)d->ptrs_bytes);
     if (r) return r;
     const u8 *src_el = (const u8 *)d->elems_alloc, *src_ptr = (const u8 *)d->ptrs_alloc;
+    if (via_ipc == 2) {
+        // elems_alloc / ptrs_alloc are HOST copies of the two slices (nlzm_mf_read_segment on the exporting side)
+        cudaError_t e = cudaMemcpyAsync(bufs->el.p, src_el, (size_t)d->elems_bytes, cudaMemcpyHostToDevice, mf->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(bufs->ptr.p, src_ptr, (size_t)d->ptrs_bytes, cudaMemcpyHostToDevice, mf->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
+        if (e != cudaSuccess) return mf->fail((int)e, std::string("segment upload: ") + cudaGetErrorString(e));
+    } else {
 #ifndef NLZM_EMU
     void *open_el = nullptr, *open_ptr = nullptr;
     if (via_ipc) {
@@ -1085,6 +1149,7 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
     memcpy(bufs->el.p, src_el + d->elems_offset_bytes, (size_t)d->elems_bytes);
     memcpy(bufs->ptr.p, src_ptr + d->ptrs_offset_bytes, (size_t)d->ptrs_bytes);
 #endif
+    }
     Segment sg;
     sg.bufs = bufs;
     sg.u0 = d->origin;
@@ -1098,11 +1163,31 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
     return 0;
 }
 
+// copy of a retained segment's two slices into host memory (elems_bytes / ptrs_bytes of its descriptor):
+// the transport of last resort when neither a peer copy nor CUDA IPC is possible
+int nlzm_mf_read_segment(nlzm_mf *mf, uint32_t index, void *elems_host, void *ptrs_host) {
+    if (!mf || !elems_host || !ptrs_host) return NLZM_MF_E_ARG;
+    Turn turn(mf);
+    if (index >= mf->segs.size()) return mf->fail(NLZM_MF_E_ARG, "no such segment");
+#ifndef NLZM_EMU
+    cudaSetDevice(mf->device);
+#endif
+    const Segment &sg = mf->segs[index];
+    cudaError_t e = cudaMemcpyAsync(elems_host, sg.elems(), (size_t)sg.n_elems * sizeof(Elem), cudaMemcpyDeviceToHost, mf->st);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(ptrs_host, (const u8 *)sg.bufs->ptr.p + (sg.pos_b - sg.ptr_pos0) * sizeof(PtrEntry),
+                            (size_t)(sg.pos_e - sg.pos_b) * sizeof(PtrEntry), cudaMemcpyDeviceToHost, mf->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
+    if (e != cudaSuccess) return mf->fail((int)e, std::string("read_segment: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 int nlzm_mf_drop_segments(nlzm_mf *mf) {
     if (!mf) return NLZM_MF_E_ARG;
-    std::lock_guard<std::mutex> lock(mf->mu);
+    Turn turn(mf);
     mf->segs.clear();
     mf->fresh.clear();
+    mf->prep_fresh.clear();
     mf->prepared = false;
     return 0;
 }
@@ -1135,7 +1220,7 @@ int nlzm_mf_get_kernel_times(nlzm_mf_kernel_time *out, uint32_t cap, uint32_t *n
 
 int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value) {
     if (!mf || !key) return NLZM_MF_E_ARG;
-    std::lock_guard<std::mutex> lock(mf->mu);
+    Turn turn(mf);
     const std::string k(key);
     if (k == "ht_margin") { mf->ht_margin = value; return 0; }
     if (k == "retain") { mf->retain = value != 0; if (!mf->retain) mf->segs.clear(); return 0; }

@@ -109,11 +109,25 @@ class MatchFinders:
         self._check(self._L.nlzm_mf_export_segments(self._h, arr, n.value, C.byref(n)), "export_segments")
         return [arr[i] for i in range(n.value)]
 
-    def import_segment(self, desc, via_ipc: bool = False) -> None:
-        """desc: a SegmentDesc from export_segments() of another engine, or its bytes (from another process)"""
+    def import_segment(self, desc, via: int = 0, host_copy=None) -> None:
+        """desc: a SegmentDesc from export_segments() of another engine, or its bytes (from another process).
+        via 0: same process (peer copy), 1: CUDA IPC handles, 2: host_copy = (elems, ptrs) numpy byte arrays"""
         if isinstance(desc, (bytes, bytearray)):
             desc = _lib.SegmentDesc.from_buffer_copy(desc)
-        self._check(self._L.nlzm_mf_import_segment(self._h, C.byref(desc), int(via_ipc)), "import_segment")
+        if host_copy is not None:
+            via = 2
+            d = _lib.SegmentDesc.from_buffer_copy(bytes(desc))
+            d.elems_alloc = host_copy[0].ctypes.data
+            d.ptrs_alloc = host_copy[1].ctypes.data
+            desc = d
+        self._check(self._L.nlzm_mf_import_segment(self._h, C.byref(desc), int(via)), "import_segment")
+
+    def read_segment(self, index: int, desc):
+        """host copies (elems, ptrs) of retained segment `index` (desc = export_segments()[index])"""
+        el = np.empty(int(desc.elems_bytes), np.uint8)
+        pt = np.empty(int(desc.ptrs_bytes), np.uint8)
+        self._check(self._L.nlzm_mf_read_segment(self._h, index, el.ctypes.data, pt.ctypes.data), "read_segment")
+        return el, pt
 
     def drop_segments(self) -> None:
         self._check(self._L.nlzm_mf_drop_segments(self._h), "drop_segments")

@@ -37,3 +37,74 @@ def concat_views(parts):
         ds.append(st["dist"])
         ls.append(st["len"])
     return np.concatenate(offs), np.concatenate(ds).astype(np.uint32), np.concatenate(ls).astype(np.uint16)
+
+
+# --------------------------------------------------------------------------------------------------
+# Position sharding with the segment hand-over (include/nlzm_mf.h "segments"): every rank ranks and
+# merges ITS OWN positions only; the window behind its range comes from the ranks that own it, as a
+# one-sided copy of their sorted blocks + pointers (peer copy / CUDA IPC over NVLink, or staged through
+# the host). No collective on the data path: the only group call exchanges a few hundred bytes of
+# descriptors (and doubles as the "neighbours are ready" barrier).
+# --------------------------------------------------------------------------------------------------
+
+def blocks_for(begin: int, end: int, window: int, max_block: int = 1 << 28) -> list[tuple[int, int]]:
+    """engine calls for [begin, end): blocks of at least one window (a later block then only needs the blocks
+    of its own shard behind it) and at most 2^28 positions"""
+    blk = min(max_block, max(window, 1 << 27))
+    return split_blocks(begin, end, blk)
+
+
+class ShardedFind:
+    """Drives one engine (one rank) through   prepare(first block) -> later blocks -> exchange -> first block.
+
+    transport: "ipc" (other processes on the same box), "peer" (engines of one process), "host" (staged copy)
+    group:     torch.distributed group used for the descriptor exchange (None = single rank)
+    """
+
+    def __init__(self, mf, rank: int, world: int, window: int, group=None, transport: str = "ipc"):
+        self.mf, self.rank, self.world, self.W, self.group, self.transport = mf, rank, world, window, group, transport
+        self.imported_bytes = 0
+
+    def _exchange(self, payload):
+        import torch.distributed as dist
+        out = [None] * self.world
+        dist.all_gather_object(out, payload, group=self.group)
+        return out
+
+    def run(self, blocks, find):
+        """blocks: this rank's engine calls in position order; find(b, e, i) does the engine call and consumes
+        its result. Returns the list of find() results in block order."""
+        mf = self.mf
+        if self.world == 1:
+            return [find(b, e, i) for i, (b, e) in enumerate(blocks)]
+        first = blocks[0]
+        need_from = max(0, first[0] - (self.W - 1))
+        mf.prepare(*first)
+        later = [find(b, e, i + 1) for i, (b, e) in enumerate(blocks[1:])]
+        descs = mf.export_segments()
+        mine = []
+        for i, d in enumerate(descs):
+            item = {"desc": bytes(d), "pos": (int(d.pos_begin), int(d.pos_end))}
+            mine.append(item)
+        if self.transport == "host":
+            # staged copy: every rank publishes the slices the next ranks can reach
+            nxt = blocks[-1][1]
+            for i, (d, item) in enumerate(zip(descs, mine)):
+                if item["pos"][1] > nxt - (self.W - 1) - 1:
+                    el, pt = mf.read_segment(i, d)
+                    item["host"] = (el, pt)
+        everyone = self._exchange(mine)
+        self.imported_bytes = 0
+        for q in range(self.rank - 1, -1, -1):
+            for item in everyone[q]:
+                pb, pe = item["pos"]
+                if pe > need_from and pe <= first[0]:
+                    if self.transport == "host":
+                        mf.import_segment(item["desc"], host_copy=item["host"])
+                    else:
+                        mf.import_segment(item["desc"], via=1 if self.transport == "ipc" else 0)
+                    self.imported_bytes += (pe - pb) * 64
+        # nobody may recycle a buffer a neighbour is still reading
+        import torch.distributed as dist
+        dist.barrier(group=self.group)
+        return [find(first[0], first[1], 0)] + later

@@ -189,3 +189,41 @@ def test_emu_sharded_engines_import_segments(emu_lib, orc, world):
     finally:
         for mf in engines:
             mf.Release()
+
+
+def test_emu_sharded_multi_block_ranges(emu_lib, orc):
+    """a shard larger than one engine call: its first block is prepared, the later blocks are found (they query the
+    blocks before them), the neighbour's segments arrive, and the first block finishes last"""
+    from nlzm_b200 import synth, sharding
+    from nlzm_b200.matchfinder import MatchFinders
+    x = synth.text(150_000, 19)
+    hb = 15
+    W = 1 << hb
+    ref = orc.find(x, hb, orc.F_ALL)
+    world = 2
+    engines = [MatchFinders(emu_lib) for _ in range(world)]
+    ranges = [sharding.shard_range(x.size, r, world) for r in range(world)]
+    blocks = [sharding.split_blocks(b, e, 34_000) for (b, e) in ranges]      # blocks of at least one window
+    parts = []
+    try:
+        for mf, bl in zip(engines, blocks):
+            mf.Init(hb, x)
+            mf.prepare(*bl[0])
+            for i, (b, e) in enumerate(bl[1:]):
+                off, st = mf.FindAndUpdate(b, e, slot=i & 1)
+                assert mf.stats().segments_queried > 0
+                parts.append((b, e, off, st))
+        descs = [mf.export_segments() for mf in engines]
+        for r, (mf, bl) in enumerate(zip(engines, blocks)):
+            b0 = bl[0][0]
+            for q in range(r):
+                for d in descs[q]:
+                    if d.pos_end > max(0, b0 - (W - 1)) and d.pos_end <= b0:
+                        mf.import_segment(bytes(d))
+            off, st = mf.FindAndUpdate(*bl[0])
+            parts.append((bl[0][0], bl[0][1], off, st))
+        got = sharding.concat_views(parts)
+        assert orc.csr_equal(ref, got), orc.first_diff(ref, got)
+    finally:
+        for mf in engines:
+            mf.Release()

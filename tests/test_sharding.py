@@ -1,6 +1,7 @@
 """Multi-GPU host logic on CPU: one process per rank (gloo, world_size 2), positions sharded, no
-data-path collective — each rank finds its own range (with the window halo behind it), rank 0 gathers
-the per-rank results and they must equal the whole-file oracle."""
+data-path collective — each rank ranks and merges its own range only and takes the sorted blocks of the window
+behind it from the rank that owns them (sharding.ShardedFind, staged through the host here); rank 0 gathers the
+per-rank results and they must equal the whole-file oracle."""
 import os
 import sys
 
@@ -23,11 +24,20 @@ def _worker(rank, world, port, q):
     emu = _lib.bind_prototypes(C.CDLL(os.path.join(ROOT, "tests", "emu", "libnlzm_mf_emu.so")))
     x = synth.longrange(110_000, 91)                     # replicated input
     b, e = sharding.shard_range(x.size, rank, world)
+    mine = []
     with MatchFinders(emu) as mf:
         mf.Init(15, x)
-        off, st = mf.FindAndUpdate(b, e)
+        # the segment hand-over protocol of the bench, staged through the host (two CPU processes share no memory)
+        sf = sharding.ShardedFind(mf, rank, world, 1 << 15, group=None, transport="host")
+        blocks = sharding.split_blocks(b, e, 40_000)
+
+        def find(bb, ee, i):
+            off, st = mf.FindAndUpdate(bb, ee, slot=i & 1)
+            mine.append((bb, ee, off, st, int(mf.stats().segments_queried)))
+        sf.run(blocks, find)
+    assert all(u > 0 for (bb, _, _, _, u) in mine if bb > 0), [m[4] for m in mine]
     parts = [None] * world
-    dist.gather_object((b, e, off, st), parts if rank == 0 else None, dst=0)
+    dist.gather_object([m[:4] for m in mine], parts if rank == 0 else None, dst=0)
     t = torch.tensor([float(rank + 1)])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)             # the bench's max-over-ranks timing pattern
     if rank == 0:
@@ -49,7 +59,7 @@ def test_two_rank_sharding(emu_lib, orc):
         assert p.exitcode == 0
     assert tmax == 2.0
     x = synth.longrange(110_000, 91)
-    off, dist_, ln = sharding.concat_views([(b, e, o, s) for (b, e, o, s) in parts])
+    off, dist_, ln = sharding.concat_views([p for rank_parts in parts for p in rank_parts])
     ref = orc.find(x, 15, orc.F_ALL)
     assert orc.csr_equal(ref, (off, dist_, ln))
 
