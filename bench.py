@@ -274,7 +274,7 @@ def run_ours(args):
     ok = 1
     try:
         step_resident()
-    except MatchFinderError as ex:                          # e.g. CUDA IPC not permitted in this container
+    except (MatchFinderError, RuntimeError) as ex:          # e.g. CUDA IPC not permitted in this container
         ok = 0
         sys.stderr.write(f"[bench rank {rank}] segment hand-over failed ({ex}); falling back to halo re-ranking\n")
     if world > 1:
@@ -342,7 +342,7 @@ def run_ours(args):
         return d2h
     e2e_ok = len(blocks) <= 2
     if e2e_ok:
-        step_e2e_all(1)
+        step_e2e_all(2)                                      # both result slots: their pinned buffers are allocated here
     barrier()
     t0 = time.perf_counter()
     d2h_bytes = step_e2e_all(args.steps) if e2e_ok else 0
@@ -366,7 +366,10 @@ def run_ours(args):
     # ==============================================================================================
     c3 = None
     if args.c3:
-        c3 = run_c3(args, torch, dist, dev, local, rank, world, gloo, replicate, barrier, flush, state)
+        try:
+            c3 = run_c3(args, torch, dist, dev, local, rank, world, gloo, replicate, barrier, flush, state)
+        except (MatchFinderError, RuntimeError) as ex:      # raised on every rank at the same protocol point
+            c3 = {"unavailable": f"{type(ex).__name__}: {ex}"[:300]}
 
     if rank == 0:
         ms_per_step = wall_ms / args.steps

@@ -71,12 +71,21 @@ typedef struct {
 } nlzm_mf_geometry;
 
 /* One staircase step == one MatchTable::Update(dist, len). Six bytes (three u16, no padding): the
- * candidate records are what crosses PCIe, 3.5 of them per input byte on text. */
+ * candidate records are what crosses PCIe, 3.5 of them per input byte on text. The spare bits carry what
+ * the parser needs before it can price the candidate (NLZM.cpp:1556-1596), computed on the GPU:
+ *   dist_lo            distance bits 0..15
+ *   dist_hi  0..11     distance bits 16..27        12..13  shortest length allowed at this distance - 2
+ *                                                          (get_match_min, NLZM.cpp:813-821)
+ *   len      0..8      length (2..264)             9..14   distance slot of the stream's distance code
+ *                                                          (NLZM.cpp:1219-1236; raw bits = slot < 4 ? 0 : slot/2 - 1) */
 typedef struct {
-    uint16_t dist_lo, dist_hi;     /* distance = dist_lo | dist_hi << 16 */
+    uint16_t dist_lo, dist_hi;
     uint16_t len;
 } nlzm_mf_step;
-#define NLZM_MF_STEP_DIST(s) ((uint32_t)(s).dist_lo | ((uint32_t)(s).dist_hi << 16))
+#define NLZM_MF_STEP_DIST(s) ((uint32_t)(s).dist_lo | (((uint32_t)(s).dist_hi & 0x0FFFu) << 16))
+#define NLZM_MF_STEP_LEN(s) ((uint32_t)(s).len & 0x1FFu)
+#define NLZM_MF_STEP_SLOT(s) (((uint32_t)(s).len >> 9) & 0x3Fu)
+#define NLZM_MF_STEP_SHORTEST(s) (2u + (((uint32_t)(s).dist_hi >> 12) & 3u))
 
 /* Candidates of positions [begin, end): position a owns steps[offsets[a-begin] .. offsets[a-begin+1]),
  * strictly increasing in len and dist. Pointers are HOST pointers into pinned memory owned by the

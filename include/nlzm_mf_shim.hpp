@@ -92,7 +92,7 @@ struct GpuMatchFinders {
         if (abs_pos < cur_begin) { printf("Assert failed nlzm_mf position %llu before the current block\n", (unsigned long long)abs_pos); exit(-1); }
         const uint64_t i = abs_pos - cur_begin;
         const uint32_t b = view.offsets[i], e = view.offsets[i + 1];
-        for (uint32_t s = b; s < e; s++) mt.Update(NLZM_MF_STEP_DIST(view.steps[s]), view.steps[s].len);
+        for (uint32_t s = b; s < e; s++) mt.Update(NLZM_MF_STEP_DIST(view.steps[s]), (uint16_t)NLZM_MF_STEP_LEN(view.steps[s]));
         steps_served += e - b;
     }
 

@@ -642,11 +642,13 @@ NLZM_KERNEL_1D(dc_link, DcParams)
 // A find keeps its final sorted blocks and pointers ("segments"); a later find whose range follows does not
 // re-rank and re-merge the window behind it but queries those segments. Ranks of different finds (or GPUs) are
 // not comparable, so the merge order comes from the suffixes themselves: the carried 18-byte prefixes first, the
-// text beyond them when those tie. Both sides are sorted by an order that refines "first 264 symbols, end of file
-// below every byte", so merging them under that order is well defined; ties put the (earlier) segment side first,
-// which is what the rank order does with equal ranks.
+// text beyond them when those tie. Both sides are sorted by an order that refines "first 264 bytes, zero-padded
+// past the end of the file", so merging them under that order is well defined; ties put the (earlier) segment side
+// first, which is what the rank order does with equal ranks.
 
-// does segment element l go before own element r?
+// does segment element l go before own element r? Order of the first 264 bytes with the text zero-padded past
+// its end — the preorder both rank orders refine (prefix doubling compares zero-padded 8-byte blocks; a block
+// that starts past the end only sorts below a block of real zeros, which this order leaves as a tie).
 DEV bool x_left_first(const DcParams &p, const Elem &l, const Elem &r) {
     u64 d = l.p0 ^ r.p0;
     if (d) { const u32 sh = (u32)nlzm_ctz64(d) & ~7u; return ((l.p0 >> sh) & 0xFF) < ((r.p0 >> sh) & 0xFF); }
@@ -654,15 +656,21 @@ DEV bool x_left_first(const DcParams &p, const Elem &l, const Elem &r) {
     if (d) { const u32 sh = (u32)nlzm_ctz64(d) & ~7u; return ((l.p1 >> sh) & 0xFF) < ((r.p1 >> sh) & 0xFF); }
     d = (l.tail ^ r.tail) & 0xFFFFull;
     if (d) { const u32 sh = (u32)nlzm_ctz64(d) & ~7u; return ((l.tail >> sh) & 0xFF) < ((r.tail >> sh) & 0xFF); }
-    // 18 equal bytes (bytes past the end of the file read as zero padding). r is the later position: it reaches
-    // the end of the file first, and a suffix that ends sorts below one that goes on.
+    // 18 equal bytes (the carried prefixes are zero-padded already). r is the later position.
     const u64 pl = p.seg_u0 + (u32)l.key, pr = p.u0 + (u32)r.key;
-    const u64 left_r = p.g.flen - pr;
-    if (left_r <= NLZM_ELEM_PREFIX) return false;
-    const u32 lim = left_r < NLZM_MATCH_MAX ? (u32)left_r : NLZM_MATCH_MAX;
-    const u32 m = NLZM_ELEM_PREFIX + lcp_cap(p.x, pl + NLZM_ELEM_PREFIX, pr + NLZM_ELEM_PREFIX, lim - NLZM_ELEM_PREFIX);
-    if (m < lim) return p.x[pl + m] < p.x[pr + m];
-    return lim == NLZM_MATCH_MAX;               // equal to the full depth: segment side first; r ended: r first
+    const u64 left_r = p.g.flen - pr, left_l = p.g.flen - pl;
+    u32 m = NLZM_ELEM_PREFIX;
+    const u32 lim = left_r < NLZM_MATCH_MAX ? (u32)left_r : NLZM_MATCH_MAX;       // bytes r really has
+    if (lim > NLZM_ELEM_PREFIX) {
+        m += lcp_cap(p.x, pl + NLZM_ELEM_PREFIX, pr + NLZM_ELEM_PREFIX, lim - NLZM_ELEM_PREFIX);
+        if (m < lim) return p.x[pl + m] < p.x[pr + m];
+    } else {
+        m = lim;                                                                 // r ends inside the prefix
+    }
+    // r is all padding from here on: l goes first only if it is zero up to the full depth as well
+    const u32 end_l = left_l < NLZM_MATCH_MAX ? (u32)left_l : NLZM_MATCH_MAX;
+    for (; m < end_l; m++) if (p.x[pl + m]) return false;
+    return true;
 }
 
 DEV u32 x_merge_path(const DcParams &p, const Elem *L, u32 l_len, const Elem *R, u32 r_len, u32 d) {

@@ -229,10 +229,12 @@ struct nlzm_mf {
     void to_pool(DevBuf &b) {
         if (!b.p) return;
         std::lock_guard<std::mutex> l(pool_mu);
-        if (pool.size() >= 6) {                       // keep the largest few
+        size_t held = 0;
+        for (const DevBuf &q : pool) held += q.bytes;
+        if (pool.size() >= 4 || held + b.bytes > (48ull << 30)) {     // keep a few, and the largest of them
             size_t small = 0;
             for (size_t i = 1; i < pool.size(); i++) if (pool[i].bytes < pool[small].bytes) small = i;
-            if (pool[small].bytes < b.bytes) std::swap(pool[small], b);
+            if (!pool.empty() && pool[small].bytes < b.bytes) std::swap(pool[small], b);
             cudaFree(b.p);
         } else {
             pool.push_back(b);
@@ -1112,6 +1114,8 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
 #endif
     auto bufs = std::make_shared<SegBufs>();
     bufs->owner = mf;
+    // the level-array work buffers are idle between finds: lend them to the imports (stage T takes them back)
+    mf->to_pool(mf->el[0]); mf->to_pool(mf->el[1]); mf->to_pool(mf->ptr);
     int r = mf->ensure_pooled(bufs->el, (size_t)d->elems_bytes);
     if (r == 0) r = mf->ensure_pooled(bufs->ptr, (size_t)d->ptrs_bytes);
     if (r) return r;

@@ -75,7 +75,12 @@ class BlockFeed {
         const uint64_t i = abs_pos - view_.begin;
         const nlzm_mf_step *s = view_.steps + view_.offsets[i];
         const uint32_t n = view_.offsets[i + 1] - view_.offsets[i];
-        st.merge_steps(n, [s](uint32_t j) { return NLZM_MF_STEP_DIST(s[j]); }, [s](uint32_t j) { return (uint32_t)s[j].len; });
+        // distance + the engine's pre-pricing (slot, shortest length) as one staircase entry
+        st.merge_steps(n,
+                       [s](uint32_t j) {
+                           return nlzm_host::candidate_entry(NLZM_MF_STEP_DIST(s[j]), NLZM_MF_STEP_SLOT(s[j]) | ((NLZM_MF_STEP_SHORTEST(s[j]) - 2u) << 6));
+                       },
+                       [s](uint32_t j) { return NLZM_MF_STEP_LEN(s[j]); });
         steps_served += n;
     }
 

@@ -33,35 +33,48 @@ constexpr uint32_t kSegmentMax = 1u << 12;
 constexpr uint32_t kLongEnough = 64;         // carried candidate this long: ask the engine sparsely
 constexpr uint32_t kSparseMask = 7;
 
+// What the parser needs from a candidate's distance before it can price it, packed next to the distance so that
+// both move through the staircase together: bits 0..5 distance slot, bits 6..7 shortest length - 2. The engine
+// computes it on the GPU for every step it emits (nlzm_mf_step); candidates that come from the host
+// (one Update per step through the reference-shaped interface) get it from split_distance / shortest_len.
+static inline uint32_t candidate_code(uint32_t dist) {
+    return split_distance(dist).slot | ((shortest_len(dist) - kLenMin) << 6);
+}
+static inline uint64_t candidate_entry(uint32_t dist, uint32_t code) { return ((uint64_t)dist << 32) | code; }
+
 class Staircase {
   public:
     uint32_t top = 0;                                 // longest known length (0 = nothing)
     Staircase() : buf_(kSlide + kLenMax + 2) {}
-    uint32_t &operator[](uint32_t len) { return buf_[at_ + len]; }
+    // entry of a length: distance in the high word (entries compare like distances), its code in the low word
+    uint64_t entry(uint32_t len) const { return buf_[at_ + len]; }
+    uint32_t operator[](uint32_t len) const { return (uint32_t)(buf_[at_ + len] >> 32); }
+    void set(uint32_t len, uint64_t e) { buf_[at_ + len] = e; }
 
     // the interface the engine shim drives (MatchTable::Update, NLZM.cpp:848-863)
     void Update(uint32_t dist, uint16_t len) {
-        uint32_t *d = &buf_[at_];
+        const uint64_t e = candidate_entry(dist, candidate_code(dist));
+        uint64_t *d = &buf_[at_];
         uint32_t known = top < len ? top : len;
         for (uint32_t i = 0; i <= known; i++)
-            if (dist < d[i]) d[i] = dist;
-        for (uint32_t i = known + 1; i <= len; i++) d[i] = dist;
+            if (e < d[i]) d[i] = e;
+        for (uint32_t i = known + 1; i <= len; i++) d[i] = e;
         if (len > top) top = len;
     }
     // A whole position's steps in one pass: the same result as Update(dist_j, len_j) for j = 0..n-1
     // when the steps are strictly increasing in len and dist (the engine's contract, nlzm_mf.h) —
     // step j then only matters for lengths above len_{j-1}, so the work is O(longest) instead of
-    // O(sum of lengths).
-    template <class DistOf, class LenOf> void merge_steps(uint32_t n, DistOf dist_of, LenOf len_of) {
+    // O(sum of lengths). entry_of(j) = candidate_entry(distance, code) of step j.
+    template <class EntryOf, class LenOf> void merge_steps(uint32_t n, EntryOf entry_of, LenOf len_of) {
         if (n == 0) return;
-        uint32_t *d = &buf_[at_];
+        uint64_t *d = &buf_[at_];
         uint32_t i = 0, len = 0;
         for (uint32_t j = 0; j < n; j++) {
-            const uint32_t dist = dist_of(j);
+            const uint64_t e = entry_of(j);
             len = len_of(j);
             const uint32_t known = top < len ? top : len;
-            for (; i <= known; i++) d[i] = dist < d[i] ? dist : d[i];
-            for (; i <= len; i++) d[i] = dist;
+            for (; i <= known; i++) d[i] = e < d[i] ? e : d[i];
+            for (; i <= len; i++) d[i] = e;
         }
         if (len > top) top = len;
     }
@@ -70,14 +83,14 @@ class Staircase {
         if (top <= 1) { top = 0; return; }
         --top;
         if (++at_ == kSlide) {
-            memmove(&buf_[0], &buf_[at_], (top + 1) * sizeof(uint32_t));
+            memmove(&buf_[0], &buf_[at_], (top + 1) * sizeof(uint64_t));
             at_ = 0;
         }
     }
 
   private:
     static constexpr uint32_t kSlide = 1u << 14;
-    std::vector<uint32_t> buf_;
+    std::vector<uint64_t> buf_;
     uint32_t at_ = 0;
 };
 
@@ -131,11 +144,11 @@ template <class Finders> class SegmentParser {
             st.advance();
             if (st.top > 0) {
                 // re-extend the longest carried candidate against the text
-                const uint32_t dist = st[st.top];
-                const uint8_t *src = here + p - dist;
+                const uint64_t longest = st.entry(st.top);
+                const uint8_t *src = here + p - (uint32_t)(longest >> 32);
                 while (st.top < kLenMax && visible > st.top + p && src[st.top] == here[p + st.top]) {
                     ++st.top;
-                    st[st.top] = dist;
+                    st.set(st.top, longest);
                 }
             }
             if ((st.top < kLongEnough || !(p & kSparseMask)) && visible >= 4 + p)
@@ -151,16 +164,18 @@ template <class Finders> class SegmentParser {
 
             uint32_t met = 0;                         // recent distances seen among the candidates
             const uint32_t step = top >= kLenMin + 16 ? (top - kLenMin) >> 4 : 1;
-            uint32_t run_dist = 0, shortest = 0, slot = 0, raw_price = 0;     // per run of equal distances
+            uint64_t run = 0;                                                 // per run of equal distances
+            uint32_t dist = 0, shortest = 0, slot = 0, raw_price = 0;
             int recent_index = -1;
             for (uint32_t len = top; len >= kLenMin; len = len > step ? len - step : 0) {
-                const uint32_t dist = st[len];
-                if (dist != run_dist) {
-                    run_dist = dist;
-                    shortest = shortest_len(dist);
-                    const DistCode dc = split_distance(dist);
-                    slot = dc.slot;
-                    raw_price = dc.raw_bits << kPriceShift;
+                const uint64_t e = st.entry(len);
+                if (e != run) {
+                    // slot and shortest length come with the candidate (computed on the GPU)
+                    run = e;
+                    dist = (uint32_t)(e >> 32);
+                    slot = (uint32_t)e & 63u;
+                    shortest = kLenMin + (((uint32_t)e >> 6) & 3u);
+                    raw_price = (slot < 4 ? 0u : (slot >> 1) - 1u) << kPriceShift;
                     recent_index = from_recent.index_of(dist);
                 }
                 if (len < shortest) continue;

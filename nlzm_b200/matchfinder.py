@@ -175,9 +175,14 @@ class MatchFinders:
 def unpack_steps(raw: np.ndarray) -> np.ndarray:
     """raw 6-byte records (copy=False views) -> STEP_DTYPE array with a 32-bit `dist` field"""
     steps = np.empty(raw.size, dtype=STEP_DTYPE)
-    steps["dist"] = raw["dist_lo"].astype(np.uint32) | (raw["dist_hi"].astype(np.uint32) << 16)
-    steps["len"] = raw["len"]
+    steps["dist"] = raw["dist_lo"].astype(np.uint32) | ((raw["dist_hi"].astype(np.uint32) & 0x0FFF) << 16)
+    steps["len"] = raw["len"] & 0x1FF          # bits 9..14 carry the distance slot, dist_hi bits 12..13 the shortest length
     return steps
+
+
+def unpack_prepricing(raw: np.ndarray):
+    """(distance slot, shortest length) the engine computed for every step"""
+    return ((raw["len"] >> 9) & 0x3F).astype(np.uint8), (2 + ((raw["dist_hi"] >> 12) & 3)).astype(np.uint8)
 
 
 def profile(enable: bool, lib=None) -> None:

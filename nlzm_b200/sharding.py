@@ -71,40 +71,58 @@ class ShardedFind:
         dist.all_gather_object(out, payload, group=self.group)
         return out
 
+    def _agree(self, err):
+        """every rank learns whether any rank failed in the phase just finished (also a barrier)"""
+        errs = [e for e in self._exchange(err) if e]
+        if errs:
+            raise RuntimeError("sharded find failed on some rank: " + "; ".join(errs))
+
     def run(self, blocks, find):
         """blocks: this rank's engine calls in position order; find(b, e, i) does the engine call and consumes
-        its result. Returns the list of find() results in block order."""
+        its result. Returns the list of find() results in block order. A failure on any rank raises on every
+        rank at the same point of the protocol (no rank is left waiting in a group call)."""
         mf = self.mf
         if self.world == 1:
             return [find(b, e, i) for i, (b, e) in enumerate(blocks)]
         first = blocks[0]
         need_from = max(0, first[0] - (self.W - 1))
-        mf.prepare(*first)
-        later = [find(b, e, i + 1) for i, (b, e) in enumerate(blocks[1:])]
-        descs = mf.export_segments()
-        mine = []
-        for i, d in enumerate(descs):
-            item = {"desc": bytes(d), "pos": (int(d.pos_begin), int(d.pos_end))}
-            mine.append(item)
-        if self.transport == "host":
-            # staged copy: every rank publishes the slices the next ranks can reach
-            nxt = blocks[-1][1]
-            for i, (d, item) in enumerate(zip(descs, mine)):
-                if item["pos"][1] > nxt - (self.W - 1) - 1:
-                    el, pt = mf.read_segment(i, d)
-                    item["host"] = (el, pt)
-        everyone = self._exchange(mine)
+        err, later, mine = None, [], []
+        try:
+            mf.prepare(*first)
+            later = [find(b, e, i + 1) for i, (b, e) in enumerate(blocks[1:])]
+            descs = mf.export_segments()
+            for d in descs:
+                mine.append({"desc": bytes(d), "pos": (int(d.pos_begin), int(d.pos_end))})
+            if self.transport == "host":
+                # staged copy: every rank publishes the slices the next ranks can reach
+                nxt = blocks[-1][1]
+                for i, (d, item) in enumerate(zip(descs, mine)):
+                    if item["pos"][1] > nxt - (self.W - 1) - 1:
+                        item["host"] = mf.read_segment(i, d)
+        except Exception as ex:  # noqa: BLE001 - reported to every rank below
+            err = f"rank {self.rank}: {ex}"
+        everyone = self._exchange({"err": err, "segs": mine})
+        errs = [p["err"] for p in everyone if p["err"]]
+        if errs:
+            raise RuntimeError("sharded find failed on some rank: " + "; ".join(errs))
         self.imported_bytes = 0
-        for q in range(self.rank - 1, -1, -1):
-            for item in everyone[q]:
-                pb, pe = item["pos"]
-                if pe > need_from and pe <= first[0]:
-                    if self.transport == "host":
-                        mf.import_segment(item["desc"], host_copy=item["host"])
-                    else:
-                        mf.import_segment(item["desc"], via=1 if self.transport == "ipc" else 0)
-                    self.imported_bytes += (pe - pb) * 64
-        # nobody may recycle a buffer a neighbour is still reading
-        import torch.distributed as dist
-        dist.barrier(group=self.group)
-        return [find(first[0], first[1], 0)] + later
+        try:
+            for q in range(self.rank - 1, -1, -1):
+                for item in everyone[q]["segs"]:
+                    pb, pe = item["pos"]
+                    if pe > need_from and pe <= first[0]:
+                        if self.transport == "host":
+                            mf.import_segment(item["desc"], host_copy=item["host"])
+                        else:
+                            mf.import_segment(item["desc"], via=1 if self.transport == "ipc" else 0)
+                        self.imported_bytes += (pe - pb) * 64
+        except Exception as ex:  # noqa: BLE001
+            err = f"rank {self.rank}: {ex}"
+        self._agree(err)               # nobody may recycle a buffer a neighbour is still reading
+        try:
+            res = find(first[0], first[1], 0)
+        except Exception as ex:  # noqa: BLE001
+            err = f"rank {self.rank}: {ex}"
+            res = None
+        self._agree(err)
+        return [res] + later

@@ -30,13 +30,13 @@ static void staircase_merge_equals_updates() {
                 dists[k] = dist; lens[k] = len; k++;
             }
             for (uint32_t j = 0; j < k; j++) a.Update(dists[j], (uint16_t)lens[j]);
-            b.merge_steps(k, [&](uint32_t j) { return dists[j]; }, [&](uint32_t j) { return lens[j]; });
+            b.merge_steps(k, [&](uint32_t j) { return candidate_entry(dists[j], candidate_code(dists[j])); }, [&](uint32_t j) { return lens[j]; });
             CHECK(a.top == b.top);
-            for (uint32_t l = 1; l <= a.top; l++) CHECK(a[l] == b[l]);
+            for (uint32_t l = 1; l <= a.top; l++) CHECK(a.entry(l) == b.entry(l));
             int moves = rng() % 4;
             for (int m = 0; m < moves; m++) { a.advance(); b.advance(); }
             CHECK(a.top == b.top);
-            for (uint32_t l = 1; l <= a.top; l++) CHECK(a[l] == b[l]);
+            for (uint32_t l = 1; l <= a.top; l++) CHECK(a.entry(l) == b.entry(l));
         }
     }
     // the sliding buffer wraps (16384 advances) without losing the carried entries

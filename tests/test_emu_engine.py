@@ -227,3 +227,22 @@ def test_emu_sharded_multi_block_ranges(emu_lib, orc):
     finally:
         for mf in engines:
             mf.Release()
+
+
+@pytest.mark.parametrize("kind", ["zeros_ones", "period", "ab", "abc_runs", "words"])
+def test_emu_retained_segments_adversarial(emu_lib, orc, kind):
+    """retained segments on inputs whose suffixes tie for hundreds of bytes and end in zero runs at the end of
+    the file (the cross-segment merge order must agree with both rank orders there)"""
+    from test_fuzz import _gen
+    from nlzm_b200.matchfinder import MatchFinders
+    rng = np.random.default_rng(sum(kind.encode()) + 7)
+    for n, cuts in ((31_000, [0, 20_000, 31_000]), (50_000, [0, 9_000, 30_000, 49_700, 50_000])):
+        x = _gen(kind, n, rng)
+        if kind == "zeros_ones":
+            x[-300:] = 0
+        ref = orc.find(x, 15, orc.F_ALL)
+        with MatchFinders(emu_lib) as mf:
+            mf.Init(15, x)
+            got, used = _blocks(mf, cuts)
+        assert orc.csr_equal(ref, got), (kind, n, orc.first_diff(ref, got))
+        assert all(u > 0 for u in used[1:])

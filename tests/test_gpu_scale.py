@@ -36,9 +36,9 @@ class _Digest:
 
     def add(self, off, raw):
         self.c.update(np.diff(off.astype(np.int64)).astype(np.uint8).tobytes())
-        dist = raw["dist_lo"].astype(np.uint32) | (raw["dist_hi"].astype(np.uint32) << 16)
+        dist = raw["dist_lo"].astype(np.uint32) | ((raw["dist_hi"].astype(np.uint32) & 0x0FFF) << 16)
         self.d.update(dist.tobytes())
-        self.l.update(np.ascontiguousarray(raw["len"]).tobytes())
+        self.l.update((raw["len"] & 0x1FF).astype(np.uint16).tobytes())
         self.steps += raw.size
 
     def hexdigest(self):

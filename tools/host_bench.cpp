@@ -31,7 +31,7 @@ struct ReplayFinders {
     template <class T> void FindAndUpdate(T &st, uint64_t a) {
         const uint32_t *d = dist + off[a];
         const uint16_t *l = len + off[a];
-        st.merge_steps((uint32_t)(off[a + 1] - off[a]), [d](uint32_t j) { return d[j]; }, [l](uint32_t j) { return (uint32_t)l[j]; });
+        st.merge_steps((uint32_t)(off[a + 1] - off[a]), [d](uint32_t j) { return nlzm_host::candidate_entry(d[j], nlzm_host::candidate_code(d[j])); }, [l](uint32_t j) { return (uint32_t)l[j]; });
         served += off[a + 1] - off[a];
     }
 };
