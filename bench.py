@@ -425,6 +425,7 @@ def run_ours(args):
                                      "device_ms_per_step = CUDA events on the engine's stream",
                            "staircase_steps": all_steps, "candidate_tuples": all_tuples},
                 "device_ms_per_step": dev_ms / args.steps,
+                "host_phase_ms_rank0": {k: round(v, 2) for k, v in sf.ms.items()},
                 "stage_ms_per_step_rank0": {k: round(v / args.steps, 3) for k, v in acc.items() if k.startswith("ms_")},
                 "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": total * world, "d2h_bytes_per_step": d2h_bytes // max(args.steps, 1),
                         "ms_per_step": e2e_ms / args.steps,
@@ -486,6 +487,7 @@ def run_c3(args, torch, dist, dev, local, rank, world, gloo, replicate, barrier,
                 "handover_bytes": sf.imported_bytes}
     per_rank.update({k: round(v / steps_timed, 2) for k, v in acc.items() if k.startswith("ms_")})
     per_rank["segments_queried"] = acc.get("segments_queried", 0) // steps_timed
+    per_rank["host_phase_ms"] = {k: round(v / (steps_timed + 1), 2) for k, v in sf.ms.items()}
     t = torch.tensor([wall_ms], dtype=torch.float64, device=dev)
     allr = [per_rank]
     if world > 1:

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NLZM_CODEC_ABI_VERSION 1
+#define NLZM_CODEC_ABI_VERSION 2
 
 enum nlzm_codec_status {
     NLZM_CODEC_OK = 0,
@@ -49,6 +49,13 @@ typedef struct {
     int32_t device;             /* CUDA ordinal for the engine */
     uint32_t reserved;
     uint64_t block_len;         /* positions per engine call; 0 = max(window, 32 Mi), capped at 2^28 */
+    /* Several GPUs of one box driven by this process (struct_size tells whether these fields are present):
+     * n_devices > 1 replicates the input on devices[0..n_devices) and deals the blocks round-robin; the window
+     * behind a block is copied from the engine that owns the block before it (peer copy). `device` is ignored
+     * then and blocks are at least one window long. The stream is the same as with one device. */
+    uint32_t n_devices;
+    int32_t devices[8];
+    uint32_t reserved2;
 } nlzm_codec_config;
 
 typedef struct {

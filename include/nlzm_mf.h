@@ -158,6 +158,9 @@ int nlzm_mf_export_segments(nlzm_mf *mf, nlzm_mf_segment *out, uint32_t cap, uin
 int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *seg, int via);
 int nlzm_mf_read_segment(nlzm_mf *mf, uint32_t index, void *elems_host, void *ptrs_host);
 int nlzm_mf_drop_segments(nlzm_mf *mf);
+/* Keep only positions >= from_pos in the retained list (a straddling segment is cut down to them, order kept): what a
+ * neighbour then imports is at most one window. */
+int nlzm_mf_trim_segments(nlzm_mf *mf, uint64_t from_pos);
 
 /* Tuning / test knobs (no reference counterpart; results never depend on them):
  *   "ht_margin"      positions before a range for which the HT stage materialises per-position data

@@ -21,7 +21,8 @@ EXPORTS = ["nlzm_codec_abi_version", "nlzm_codec_compress", "nlzm_codec_decompre
 
 class CodecConfig(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("window_bits", C.c_uint32), ("device", C.c_int32),
-                ("reserved", C.c_uint32), ("block_len", C.c_uint64)]
+                ("reserved", C.c_uint32), ("block_len", C.c_uint64),
+                ("n_devices", C.c_uint32), ("devices", C.c_int32 * 8), ("reserved2", C.c_uint32)]
 
 
 class CodecStats(C.Structure):
@@ -53,7 +54,7 @@ def load():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`")
         _lib = bind_prototypes(C.CDLL(LIB_PATH))
-        if _lib.nlzm_codec_abi_version() != 1:
+        if _lib.nlzm_codec_abi_version() != 2:
             raise RuntimeError("libnlzm_codec.so ABI version mismatch")
     return _lib
 
@@ -75,11 +76,17 @@ def _as_u8(data) -> np.ndarray:
     return np.frombuffer(bytes(data), dtype=np.uint8)
 
 
-def compress(data, window_bits: int = 22, device: int = 0, block_len: int = 0, lib=None, with_stats: bool = False):
-    """bytes / uint8 array -> NLZM stream (bytes). `lib` overrides the library (tests: emulated engine)."""
+def compress(data, window_bits: int = 22, device: int = 0, block_len: int = 0, lib=None, with_stats: bool = False,
+             devices=None):
+    """bytes / uint8 array -> NLZM stream (bytes). `lib` overrides the library (tests: emulated engine).
+    devices: list of CUDA ordinals to spread the engine blocks over (same stream as with one device)."""
     L = lib or load()
     x = _as_u8(data)
     cfg = CodecConfig(C.sizeof(CodecConfig), window_bits, device, 0, block_len)
+    if devices:
+        cfg.n_devices = len(devices)
+        for i, d in enumerate(devices):
+            cfg.devices[i] = int(d)
     out, n, st = C.c_void_p(), C.c_uint64(), CodecStats()
     rc = L.nlzm_codec_compress(x.ctypes.data if x.size else None, x.size, C.byref(cfg), C.byref(out), C.byref(n), C.byref(st))
     if rc:

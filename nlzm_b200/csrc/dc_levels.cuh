@@ -28,17 +28,20 @@ extern unsigned long long nlzm_stats[16];
 #define NLZM_STAT(i, v) ((void)0)
 #endif
 
+// Greater-position pointers of one position: 16 bytes, each half = position (universe-relative, low 32 bits) |
+// link lcp << 32. No ranks: whether a new right-half neighbour r is rank-nearer to c than the pointer c holds is
+// decided by the link lcps alone — lcp(c, r) > lcp(c, pg) means nearer, < means farther, and on a tie r may be taken
+// either way: everything between r and pg in rank order then has the same lcp with c, hence with any query that
+// reaches c, and r (the later position) is the nearest of them, which is all a staircase keeps.
 struct PtrEntry {
-    u64 pg;   // key (rank<<32|pos) of the nearest element to the rank-left with a greater position in
-              // the same segment, 0 if none
-    u64 ng;   // same to the rank-right, ~0 if none
-    u16 lpg;  // lcp(this, pg) capped at 264 (0 if none): lcp(a, pg) = min(lcp(a, this), lpg) along a chain
-    u16 lng;  // lcp(this, ng)
-    u32 pad0;
-    u64 pad1; // 32 bytes = one sector per entry
+    u64 pg;   // nearest element to the rank-left with a greater position in the same segment (NLZM_PTR_NONE if none),
+              // link lcp = lcp(this, pg) capped at 264: lcp(a, pg) = min(lcp(a, this), link) along a chain
+    u64 ng;   // same to the rank-right
 };
-#define NLZM_PG_NONE 0ull
-#define NLZM_NG_NONE 0xFFFFFFFFFFFFFFFFull
+#define NLZM_PTR_NONE 0xFFFFFFFFull
+HD u64 ptr_pack(u32 pos, u32 lcp) { return (u64)pos | ((u64)lcp << 32); }
+HD u32 ptr_pos(u64 e) { return (u32)e; }
+HD u32 ptr_lcp(u64 e) { return (u32)(e >> 32) & 0xFFFFu; }
 
 // Level-array element: 32 bytes, streamed once in and once out per level.
 struct Elem {
@@ -367,9 +370,8 @@ DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         p.nxt[t0 + i] = e;
         PtrEntry pe;
         const u32 g0 = s.pg[i], g1 = s.ng[i];
-        pe.pg = g0 == NLZM_L16_NONE ? NLZM_PG_NONE : (((u64)s.rnk[g0] << 32) | (t0 + g0));
-        pe.ng = g1 == NLZM_L16_NONE ? NLZM_NG_NONE : (((u64)s.rnk[g1] << 32) | (t0 + g1));
-        pe.lpg = LPG[i]; pe.lng = LNG[i]; pe.pad0 = 0; pe.pad1 = 0;
+        pe.pg = g0 == NLZM_L16_NONE ? NLZM_PTR_NONE : ptr_pack(t0 + g0, LPG[i]);
+        pe.ng = g1 == NLZM_L16_NONE ? NLZM_PTR_NONE : ptr_pack(t0 + g1, LNG[i]);
         p.ptr[t0 + i] = pe;
     }
 }
@@ -456,7 +458,7 @@ DEV void dc_walk(const DcParams &p, const Elem &ea, u64 a_abs, u32 best_in, cons
     u32 l = first_l;
     u32 link = left ? elem_lpg(first->tail) : elem_lng(first->tail);
     bool have_entry = false;
-    PtrEntry en;
+    u64 en = 0;
     u32 pend_len = 0, pend_c = 0;
     while (l > best_in) {
         if (pend_len && l < pend_len && !(dom_l >= pend_len && dom_c > pend_c)) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
@@ -464,14 +466,13 @@ DEV void dc_walk(const DcParams &p, const Elem &ea, u64 a_abs, u32 best_in, cons
         if (l > new_best) new_best = l;
         const u32 l_next = l < link ? l : link;                // lcp never grows along the chain
         if (l_next <= best_in) break;                          // the chain ends here without touching memory
-        if (!have_entry) en = ptr[c];                          // the neighbour's pointer (its link lcp came with the element)
-        const u64 k = left ? en.pg : en.ng;
-        if (k == (left ? NLZM_PG_NONE : NLZM_NG_NONE)) break;
-        c = (u32)k;
+        if (!have_entry) en = left ? ptr[c].pg : ptr[c].ng;    // the neighbour's pointer (its link lcp came with the element)
+        if (ptr_pos(en) == (u32)NLZM_PTR_NONE) break;
+        c = ptr_pos(en);
         l = l_next;
-        en = ptr[c];
+        en = left ? ptr[c].pg : ptr[c].ng;                     // 8 bytes: where c points and the lcp of that link
         have_entry = true;
-        link = left ? en.lpg : en.lng;
+        link = ptr_lcp(en);
     }
     if (pend_len && !(dom_l >= pend_len && dom_c > pend_c)) dc_emit(p, a_abs, a_rel - pend_c, pend_len);
 }
@@ -608,31 +609,25 @@ DEV void dc_link_body(const DcParams &p, u64 idx64) {
     const Elem e = p.cur[idx];
     const u32 pos = (u32)e.key;
     const u32 u = p.corank[idx];
-    PtrEntry en = p.ptr[pos];
+    // the link lcps travel with the element, so nothing is read from ptr[]: a side that changes is one 8-byte store
+    u32 lpg = elem_lpg(e.tail), lng = elem_lng(e.tail);
     bool ch = false;
     if (u > 0) {
         const Elem r = p.cur[s.r_beg + u - 1];
-        if (r.key > en.pg) {
-            const u64 left_in_file = p.g.flen - (p.u0 + (u32)r.key);          // r is the later position
-            en.pg = r.key;
-            en.lpg = (u16)elem_pair_lcp(p, e, r, left_in_file < NLZM_MATCH_MAX ? (u32)left_in_file : NLZM_MATCH_MAX);
-            ch = true;
-        }
+        const u64 left_in_file = p.g.flen - (p.u0 + (u32)r.key);              // r is the later position
+        const u32 l = elem_pair_lcp(p, e, r, left_in_file < NLZM_MATCH_MAX ? (u32)left_in_file : NLZM_MATCH_MAX);
+        if (l >= lpg) { p.ptr[pos].pg = ptr_pack((u32)r.key, l); lpg = l; ch = true; }
     }
     if (u < s.r_len) {
         const Elem r = p.cur[s.r_beg + u];
-        if (r.key < en.ng && (u32)(r.key >> 32) != NLZM_RANK_PAD) {
+        if ((u32)(r.key >> 32) != NLZM_RANK_PAD) {
             const u64 left_in_file = p.g.flen - (p.u0 + (u32)r.key);
-            en.ng = r.key;
-            en.lng = (u16)elem_pair_lcp(p, e, r, left_in_file < NLZM_MATCH_MAX ? (u32)left_in_file : NLZM_MATCH_MAX);
-            ch = true;
+            const u32 l = elem_pair_lcp(p, e, r, left_in_file < NLZM_MATCH_MAX ? (u32)left_in_file : NLZM_MATCH_MAX);
+            if (l >= lng) { p.ptr[pos].ng = ptr_pack((u32)r.key, l); lng = l; ch = true; }
         }
     }
-    if (ch) {
-        p.ptr[pos] = en;
-        // the merged copy of this element (already written by k_dc_merge_tile) carries the link lcps too
-        p.nxt[idx + u].tail = elem_tail((u32)e.tail & 0xFFFFu, elem_best(e.tail), en.lpg, en.lng);
-    }
+    // the merged copy of this element (already written by k_dc_merge_tile) carries the link lcps too
+    if (ch) p.nxt[idx + u].tail = elem_tail((u32)e.tail & 0xFFFFu, elem_best(e.tail), lpg, lng);
 }
 NLZM_KERNEL_1D(dc_link, DcParams)
 
@@ -773,3 +768,10 @@ DEV void dc_xmerge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
     }
 }
 NLZM_KERNEL_CTA_OCC(dc_xmerge_tile, DcParams, NLZM_MT_THREADS, 3)
+
+// ---- keeping only the later positions of a segment (nlzm_mf_trim_segments): order-preserving compaction
+struct SegTrimParams { const Elem *in; Elem *out; u32 *flag; const u32 *idx; u32 cut; };   // cut: first kept position (relative)
+DEV void seg_trim_flag_body(const SegTrimParams &p, u64 i) { p.flag[i] = (u32)p.in[i].key >= p.cut ? 1u : 0u; }
+NLZM_KERNEL_1D(seg_trim_flag, SegTrimParams)
+DEV void seg_trim_move_body(const SegTrimParams &p, u64 i) { if (p.flag[i]) p.out[p.idx[i]] = p.in[i]; }
+NLZM_KERNEL_1D(seg_trim_move, SegTrimParams)

@@ -105,6 +105,8 @@ enum { SC_SUM = 0 /* u64 */, SC_RK_HITS = 8, SC_RK_INTERVALS = 9, SC_RK_VALID = 
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
+    bool shared = false;      // an IPC handle of this allocation was handed out: other processes may keep it mapped,
+                              // so it is never freed before the engine goes (it just keeps cycling through the pool)
     template <class T> T *as() const { return (T *)p; }
 };
 
@@ -175,6 +177,8 @@ struct nlzm_mf {
     DevBuf prep_tk, prep_tv;               //     found in between: the first range of a shard finishes last)
     u32 prep_nt = 0;
     float prep_ms_rank = 0, prep_ms_levels = 0, prep_ms = 0;
+    std::map<std::string, void *> ipc_open;  // importer: IPC handles already mapped into this process (closed at destroy)
+    std::map<void *, std::string> ipc_made;  // exporter: handle of an allocation (made once)
     std::vector<DevBuf> pool;              // level-array / pointer buffers waiting to be reused
     std::mutex pool_mu;
 
@@ -198,6 +202,7 @@ struct nlzm_mf {
 
     int ensure(DevBuf &b, size_t bytes) {
         if (bytes <= b.bytes) return 0;
+        if (b.p && b.shared) to_pool(b);
         if (b.p) cudaFree(b.p);
         b.p = nullptr;
         b.bytes = 0;
@@ -229,18 +234,21 @@ struct nlzm_mf {
     void to_pool(DevBuf &b) {
         if (!b.p) return;
         std::lock_guard<std::mutex> l(pool_mu);
-        size_t held = 0;
-        for (const DevBuf &q : pool) held += q.bytes;
-        if (pool.size() >= 4 || held + b.bytes > (48ull << 30)) {     // keep a few, and the largest of them
-            size_t small = 0;
-            for (size_t i = 1; i < pool.size(); i++) if (pool[i].bytes < pool[small].bytes) small = i;
-            if (!pool.empty() && pool[small].bytes < b.bytes) std::swap(pool[small], b);
+        size_t held = 0, n_free = 0;
+        for (const DevBuf &q : pool) { held += q.bytes; n_free += q.shared ? 0 : 1; }
+        if (!b.shared && (n_free >= 8 || held + b.bytes > (64ull << 30))) {     // keep a few, and the largest of them
+            size_t small = pool.size();
+            for (size_t i = 0; i < pool.size(); i++)
+                if (!pool[i].shared && (small == pool.size() || pool[i].bytes < pool[small].bytes)) small = i;
+            if (small < pool.size() && pool[small].bytes < b.bytes) std::swap(pool[small], b);
+            ipc_made.erase(b.p);
             cudaFree(b.p);
         } else {
             pool.push_back(b);
         }
         b.p = nullptr;
         b.bytes = 0;
+        b.shared = false;
     }
     void release(DevBuf &b) {
         if (b.p) cudaFree(b.p);
@@ -271,6 +279,7 @@ struct nlzm_mf {
     int stage_bt4_cross(u64 own_b, u64 own_e, const std::vector<Segment> &behind);
     void retain_fresh(u64 own_e);
     void add_segments(const std::vector<Segment> &v);
+    int trim_segments(u64 from);
     int stage_ht(u64 own_b, u64 own_e, const HtCfg &c);
     int stage_rk(u64 own_b, u64 own_e);
     int stage_merge(u64 own_b, u64 own_e, Slot &s);
@@ -527,6 +536,45 @@ void nlzm_mf::add_segments(const std::vector<Segment> &v) {
     for (Segment &o : segs) if (o.pos_e <= lo || o.pos_b >= hi) kept.push_back(o);
     for (const Segment &sg : v) kept.push_back(sg);
     segs.swap(kept);
+}
+
+// Only positions >= from stay in the retained list. A segment that straddles `from` is replaced by the sub-sequence of
+// its elements at those positions: greater-position pointers never lead to an earlier position, so the later part of
+// a segment is a complete segment of its own (what a neighbour imports is then at most one window, however the
+// exporting shard cut its blocks).
+int nlzm_mf::trim_segments(u64 from) {
+    std::vector<Segment> kept;
+    for (Segment &sg : segs) {
+        if (sg.pos_e <= from) continue;
+        if (sg.pos_b >= from) { kept.push_back(sg); continue; }
+        const u64 n = sg.n_elems;
+        CKI(ensure(aux0, n * 4)); CKI(ensure(aux1, n * 4));
+        CKI(ensure_prim(n));
+        auto bufs = std::make_shared<SegBufs>();
+        bufs->owner = this;
+        const u64 n_keep = sg.pos_e - from;
+        CKI(ensure_pooled(bufs->el, n_keep * sizeof(Elem)));
+        CKI(ensure_pooled(bufs->ptr, n_keep * sizeof(PtrEntry)));
+        SegTrimParams tp{sg.elems(), bufs->el.as<Elem>(), aux0.as<u32>(), aux1.as<u32>(), (u32)(from - sg.u0)};
+        launch_seg_trim_flag(tp, n, st);
+        CKI(prim_exclusive_sum(tmp, aux0.as<u32>(), aux1.as<u32>(), n, st));
+        launch_seg_trim_move(tp, n, st);
+        CK(cudaMemcpyAsync(bufs->ptr.p, (const u8 *)sg.bufs->ptr.p + (from - sg.ptr_pos0) * sizeof(PtrEntry), n_keep * sizeof(PtrEntry),
+                           cudaMemcpyDeviceToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        Segment t;
+        t.bufs = bufs;
+        t.u0 = sg.u0;
+        t.elem_off = 0;
+        t.n_elems = (u32)n_keep;
+        t.ptr_pos0 = from;
+        t.pos_b = from;
+        t.pos_e = sg.pos_e;
+        kept.push_back(t);
+    }
+    segs.swap(kept);
+    stats.segments_retained = (u32)segs.size();
+    return 0;
 }
 
 // after a find: its blocks join the retained list; whatever a range starting at own_e could not reach goes
@@ -961,6 +1009,10 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
     mf->fresh.clear();
     mf->prep_fresh.clear();
     mf->segs.clear();                                  // buffers go back to the pool, which is freed below
+#ifndef NLZM_EMU
+    for (auto &kv : mf->ipc_open) cudaIpcCloseMemHandle(kv.second);
+#endif
+    mf->ipc_open.clear();
     for (auto &b : mf->pool) if (b.p) cudaFree(b.p);
     mf->pool.clear();
     for (auto &s : mf->slot) {
@@ -1091,10 +1143,19 @@ int nlzm_mf_export_segments(nlzm_mf *mf, nlzm_mf_segment *out, uint32_t cap, uin
             d.ptrs_alloc = sg.bufs->ptr.p;
             d.device = mf->device;
 #ifndef NLZM_EMU
-            cudaIpcMemHandle_t h;
-            if (cudaIpcGetMemHandle(&h, sg.bufs->el.p) == cudaSuccess) { memcpy(d.ipc_elems, &h, sizeof h); d.flags |= 1u; }
-            if (cudaIpcGetMemHandle(&h, sg.bufs->ptr.p) == cudaSuccess) { memcpy(d.ipc_ptrs, &h, sizeof h); d.flags |= 2u; }
-            cudaGetLastError();
+            auto handle_of = [&](DevBuf &b, uint8_t *dst) -> bool {
+                auto it = mf->ipc_made.find(b.p);
+                if (it == mf->ipc_made.end()) {
+                    cudaIpcMemHandle_t h;
+                    if (cudaIpcGetMemHandle(&h, b.p) != cudaSuccess) { cudaGetLastError(); return false; }
+                    it = mf->ipc_made.emplace(b.p, std::string((const char *)&h, sizeof h)).first;
+                }
+                b.shared = true;
+                memcpy(dst, it->second.data(), sizeof(cudaIpcMemHandle_t));
+                return true;
+            };
+            if (handle_of(sg.bufs->el, d.ipc_elems)) d.flags |= 1u;
+            if (handle_of(sg.bufs->ptr, d.ipc_ptrs)) d.flags |= 2u;
 #endif
         }
         ++i;
@@ -1131,22 +1192,26 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
     void *open_el = nullptr, *open_ptr = nullptr;
     if (via_ipc) {
         if ((d->flags & 3u) != 3u) return mf->fail(NLZM_MF_E_ARG, "segment descriptor carries no IPC handles");
-        cudaIpcMemHandle_t h;
-        memcpy(&h, d->ipc_elems, sizeof h);
-        cudaError_t e = cudaIpcOpenMemHandle(&open_el, h, cudaIpcMemLazyEnablePeerAccess);
-        if (e == cudaSuccess) { memcpy(&h, d->ipc_ptrs, sizeof h); e = cudaIpcOpenMemHandle(&open_ptr, h, cudaIpcMemLazyEnablePeerAccess); }
-        if (e != cudaSuccess) {
-            if (open_el) cudaIpcCloseMemHandle(open_el);
-            return mf->fail((int)e, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
-        }
+        // a mapping stays open for the life of the engine: the exporter keeps the allocation alive (DevBuf::shared)
+        auto mapped = [&](const uint8_t *raw, void **out) -> cudaError_t {
+            const std::string key((const char *)raw, sizeof(cudaIpcMemHandle_t));
+            auto it = mf->ipc_open.find(key);
+            if (it != mf->ipc_open.end()) { *out = it->second; return cudaSuccess; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, raw, sizeof h);
+            cudaError_t e = cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e == cudaSuccess) mf->ipc_open.emplace(key, *out);
+            return e;
+        };
+        cudaError_t e = mapped(d->ipc_elems, &open_el);
+        if (e == cudaSuccess) e = mapped(d->ipc_ptrs, &open_ptr);
+        if (e != cudaSuccess) return mf->fail((int)e, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
         src_el = (const u8 *)open_el;
         src_ptr = (const u8 *)open_ptr;
     }
     cudaError_t e = cudaMemcpyPeerAsync(bufs->el.p, mf->device, src_el + d->elems_offset_bytes, via_ipc ? mf->device : d->device, (size_t)d->elems_bytes, mf->st);
     if (e == cudaSuccess) e = cudaMemcpyPeerAsync(bufs->ptr.p, mf->device, src_ptr + d->ptrs_offset_bytes, via_ipc ? mf->device : d->device, (size_t)d->ptrs_bytes, mf->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
-    if (open_el) cudaIpcCloseMemHandle(open_el);
-    if (open_ptr) cudaIpcCloseMemHandle(open_ptr);
     if (e != cudaSuccess) return mf->fail((int)e, std::string("segment copy: ") + cudaGetErrorString(e));
 #else
     (void)via_ipc;
@@ -1184,6 +1249,15 @@ int nlzm_mf_read_segment(nlzm_mf *mf, uint32_t index, void *elems_host, void *pt
     if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
     if (e != cudaSuccess) return mf->fail((int)e, std::string("read_segment: ") + cudaGetErrorString(e));
     return 0;
+}
+
+int nlzm_mf_trim_segments(nlzm_mf *mf, uint64_t from_pos) {
+    if (!mf) return NLZM_MF_E_ARG;
+    Turn turn(mf);
+#ifndef NLZM_EMU
+    cudaSetDevice(mf->device);
+#endif
+    return mf->trim_segments(from_pos);
 }
 
 int nlzm_mf_drop_segments(nlzm_mf *mf) {

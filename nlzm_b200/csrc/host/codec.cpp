@@ -17,6 +17,8 @@
 #include "stream_model.hpp"
 
 #include <chrono>
+#include <future>
+#include <vector>
 #include <new>
 #include <stdlib.h>
 #include <string>
@@ -115,6 +117,134 @@ class BlockFeed {
     bool pending_ = false;
 };
 
+// The same candidate source over SEVERAL engines of one process (one per GPU): the input is replicated, the
+// blocks of the file go round-robin to the engines, and the parser still sees one ascending stream of positions
+// (parse_table's loop, NLZM.cpp:1486-1543). A batch of N blocks is in flight at a time:
+//   1. every engine ranks and merges its block alone (nlzm_mf_prepare, N host threads, N GPUs busy),
+//   2. block j takes the sorted blocks of the window behind it from the engine that owns block j-1
+//      (nlzm_mf_export_segments / nlzm_mf_import_segment: a peer copy over NVLink inside one process),
+//   3. every engine finishes its block (nlzm_mf_submit) and copies the records to its pinned buffers,
+// while the parser consumes the previous batch. Blocks are at least one window long, so only block j-1 lies
+// behind block j. Result slot = parity of the batch.
+class MultiBlockFeed {
+  public:
+    ~MultiBlockFeed() { close(); }
+    uint64_t steps_served = 0, blocks_fetched = 0;
+    double ms_wait = 0;
+
+    void open(nlzm_mf_config mc, const int32_t *devices, uint32_t n_dev, uint32_t window, const uint8_t *in) {
+        flen_ = mc.file_len;
+        window_ = window;
+        uint64_t block = mc.max_range < window ? window : mc.max_range;
+        if (block > (1ull << 28)) block = 1ull << 28;
+        mc.max_range = block;
+        // block 0 is short (parsing starts almost at once); every later block is a full one
+        uint64_t first = block / 8 > (64u << 10) ? block / 8 : (64u << 10);
+        for (uint64_t b = 0; b < flen_;) {
+            const uint64_t want = b == 0 && first < block ? first : block;
+            const uint64_t e = b + want < flen_ ? b + want : flen_;
+            blocks_.push_back({b, e});
+            b = e;
+        }
+        for (uint32_t d = 0; d < n_dev; d++) {
+            mc.device = devices[d];
+            nlzm_mf *h = nullptr;
+            int rc = nlzm_mf_create(&mc, &h);
+            if (rc) throw EngineError{std::string("engine create failed on device ") + std::to_string(devices[d]) + ": " + nlzm_mf_last_error(nullptr)};
+            mf_.push_back(h);
+            check(h, nlzm_mf_set_input(h, in, mc.file_len), "set_input");
+        }
+        launch_batch(0);
+    }
+    void close() {
+        if (launching_.valid()) { try { launching_.get(); } catch (...) {} }
+        for (size_t j = 0; j < submitted_.size(); j++)
+            if (submitted_[j] && !fetched_[j]) { nlzm_mf_view v; nlzm_mf_fetch(mf_[j % mf_.size()], slot_of(j), &v); }
+        for (nlzm_mf *h : mf_) nlzm_mf_destroy(h);
+        mf_.clear();
+    }
+    template <class T> void FindAndUpdate(T &st, uint64_t abs_pos) {
+        if (abs_pos >= view_.end) {
+            auto t0 = std::chrono::steady_clock::now();
+            while (abs_pos >= view_.end) advance();
+            ms_wait += ms_since(t0);
+        }
+        const uint64_t i = abs_pos - view_.begin;
+        const nlzm_mf_step *s = view_.steps + view_.offsets[i];
+        const uint32_t n = view_.offsets[i + 1] - view_.offsets[i];
+        st.merge_steps(n,
+                       [s](uint32_t j) {
+                           return nlzm_host::candidate_entry(NLZM_MF_STEP_DIST(s[j]), NLZM_MF_STEP_SLOT(s[j]) | ((NLZM_MF_STEP_SHORTEST(s[j]) - 2u) << 6));
+                       },
+                       [s](uint32_t j) { return NLZM_MF_STEP_LEN(s[j]); });
+        steps_served += n;
+    }
+
+  private:
+    struct Range { uint64_t b, e; };
+    static void check(nlzm_mf *h, int rc, const char *what) {
+        if (rc) throw EngineError{std::string("engine ") + what + " failed (rc " + std::to_string(rc) + "): " + nlzm_mf_last_error(h)};
+    }
+    int slot_of(size_t j) const { return (int)((j / mf_.size()) & 1); }
+
+    // steps 1-3 for blocks [k*N, k*N+N), on a helper thread so that the parser keeps going
+    void launch_batch(size_t k) {
+        const size_t n_dev = mf_.size(), j0 = k * n_dev;
+        if (j0 >= blocks_.size()) return;
+        submitted_.resize(blocks_.size(), false);
+        fetched_.resize(blocks_.size(), false);
+        launching_ = std::async(std::launch::async, [this, j0, n_dev]() {
+            const size_t j1 = j0 + n_dev < blocks_.size() ? j0 + n_dev : blocks_.size();
+            std::vector<std::future<int>> prep;
+            for (size_t j = j0; j < j1; j++)
+                prep.push_back(std::async(std::launch::async, [this, j]() { return nlzm_mf_prepare(mf_[j % mf_.size()], blocks_[j].b, blocks_[j].e); }));
+            for (size_t j = j0; j < j1; j++) check(mf_[j % n_dev], prep[j - j0].get(), "prepare");
+            for (size_t j = j0 > 0 ? j0 : 1; j < j1; j++) {
+                nlzm_mf *from = mf_[(j - 1) % n_dev], *to = mf_[j % n_dev];
+                if (from == to) continue;                       // one engine: its own retained segments
+                uint32_t n_seg = 0;
+                check(from, nlzm_mf_export_segments(from, nullptr, 0, &n_seg), "export_segments");
+                std::vector<nlzm_mf_segment> segs(n_seg ? n_seg : 1);
+                check(from, nlzm_mf_export_segments(from, segs.data(), n_seg, &n_seg), "export_segments");
+                const uint64_t need = blocks_[j].b > (uint64_t)(window_ - 1) ? blocks_[j].b - (window_ - 1) : 0;
+                for (uint32_t i = 0; i < n_seg; i++)
+                    if (segs[i].pos_end > need && segs[i].pos_end <= blocks_[j].b && segs[i].pos_begin >= blocks_[j - 1].b)
+                        check(to, nlzm_mf_import_segment(to, &segs[i], 0), "import_segment");
+            }
+            for (size_t j = j0; j < j1; j++) {
+                check(mf_[j % n_dev], nlzm_mf_submit(mf_[j % n_dev], blocks_[j].b, blocks_[j].e, slot_of(j)), "submit");
+                submitted_[j] = true;
+            }
+        });
+    }
+    void advance() {
+        if (next_ >= blocks_.size()) throw EngineError{"position past the end of the input"};
+        const size_t n_dev = mf_.size();
+        if (next_ % n_dev == 0) {
+            // first block of a batch: its launch must be complete; the batch after it may start now, because
+            // the slots it will write (same parity as the batch before this one) have been consumed
+            if (launching_.valid()) launching_.get();
+            launch_batch(next_ / n_dev + 1);
+        }
+        if (!submitted_[next_]) {                               // launched by the call above (next batch) — wait for it
+            if (launching_.valid()) launching_.get();
+        }
+        check(mf_[next_ % n_dev], nlzm_mf_fetch(mf_[next_ % n_dev], slot_of(next_), &view_), "fetch");
+        fetched_[next_] = true;
+        ++next_;
+        ++blocks_fetched;
+    }
+
+    std::vector<nlzm_mf *> mf_;
+    std::vector<Range> blocks_;
+    std::vector<char> submitted_, fetched_;
+    std::future<void> launching_;
+    nlzm_mf_view view_{};
+    uint64_t flen_ = 0;
+    uint32_t window_ = 0;
+    size_t next_ = 0;
+};
+
 uint32_t read_length_excess(FrameReader &r, StreamModel &m) {
     uint32_t excess = (uint32_t)r.get(m.len_head);
     m.len_head.adapt((int)excess);
@@ -151,7 +281,6 @@ int compress_impl(const uint8_t *in, uint64_t n, const nlzm_codec_config &cfg, s
     out.push_back((uint8_t)g.frame_bits);
 
     if (n > 0) {
-        BlockFeed finders;
         nlzm_mf_config mc{};
         mc.struct_size = sizeof mc;
         mc.hist_bits = window_bits;
@@ -160,16 +289,27 @@ int compress_impl(const uint8_t *in, uint64_t n, const nlzm_codec_config &cfg, s
         mc.finder_mask = NLZM_MF_ALL;
         mc.max_range = cfg.block_len ? cfg.block_len : (g.window > (32u << 20) ? g.window : (32u << 20));
         if (mc.max_range > (1ull << 28)) mc.max_range = 1ull << 28;
-        finders.open(mc, in);
-
+        const bool has_list = cfg.struct_size >= sizeof(nlzm_codec_config) && cfg.n_devices > 1;
         EncodeCounters ec;
-        encode_stream(in, n, g.hist_bits, g.chunk_size, g.feed_size, finders, out, ec);
+        auto run = [&](auto &finders) {
+            encode_stream(in, n, g.hist_bits, g.chunk_size, g.feed_size, finders, out, ec);
+            st.steps_served = finders.steps_served;
+            st.engine_blocks = finders.blocks_fetched;
+            st.ms_engine_wait = finders.ms_wait;
+            finders.close();
+        };
+        if (has_list) {
+            if (cfg.n_devices > 8) return fail(NLZM_CODEC_E_ARG, "at most 8 devices");
+            MultiBlockFeed finders;
+            finders.open(mc, cfg.devices, cfg.n_devices, g.window, in);
+            run(finders);
+        } else {
+            BlockFeed finders;
+            finders.open(mc, in);
+            run(finders);
+        }
         st.literals = ec.literals; st.matches = ec.matches; st.reps = ec.reps;
         st.frames = ec.frames; st.parses = ec.parses;
-        st.steps_served = finders.steps_served;
-        st.engine_blocks = finders.blocks_fetched;
-        st.ms_engine_wait = finders.ms_wait;
-        finders.close();
     }
     out.insert(out.end(), 4, 0);             // a frame with zero ops ends the stream
     st.in_bytes = n;
@@ -291,6 +431,9 @@ int nlzm_codec_compress(const uint8_t *in, uint64_t in_len, const nlzm_codec_con
         if (rc) return rc;
         rc = hand_over(v, out, out_len);
         if (rc) return rc;
+    } catch (const BadCandidate &b) {
+        return fail(NLZM_CODEC_E_ENGINE, "candidate (distance " + std::to_string(b.dist) + ", length " + std::to_string(b.len) +
+                                             ") at position " + std::to_string(b.pos) + " is not a match in the text");
     } catch (const EngineError &e) {
         return fail(NLZM_CODEC_E_ENGINE, e.what);
     } catch (const std::bad_alloc &) {

@@ -15,6 +15,11 @@
 
 namespace nlzm_host {
 
+struct BadCandidate {                      // thrown by encode_stream: a (distance, length) that is not a match in the text
+    uint64_t pos;
+    uint32_t dist, len;
+};
+
 struct EncodeCounters {
     uint64_t literals = 0, matches = 0, reps = 0, frames = 0, parses = 0;
 };
@@ -91,6 +96,14 @@ void encode_stream(const uint8_t *in, uint64_t n, uint32_t hist_bits, uint32_t c
             parser.parse(model, p, p - rebase, (uint32_t)(coded_end - p), (uint32_t)(feed_end - p), cmds);
             ++ec.parses;
             for (const ParsedCommand &c : cmds) {
+                // every copy the stream is about to promise is compared with the text first (the reference does the
+                // same, NLZM.cpp:1824,1839): a wrong candidate from the engine must not become a stream that decodes
+                // to different bytes. O(n) in total.
+                if (c.kind != kLiteral) {
+                    const uint32_t dist = c.kind == kMatch ? c.value : model.recent.d[c.value];
+                    if (dist == 0 || dist > p || p + c.len > n || memcmp(in + p - dist, in + p, c.len) != 0)
+                        throw BadCandidate{p, dist, c.len};
+                }
                 write_command(frame, model, c, in[p]);
                 if (c.kind == kLiteral) { ++ec.literals; ++p; }
                 else { c.kind == kMatch ? ++ec.matches : ++ec.reps; p += c.len; }

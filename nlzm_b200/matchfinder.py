@@ -129,6 +129,10 @@ class MatchFinders:
         self._check(self._L.nlzm_mf_read_segment(self._h, index, el.ctypes.data, pt.ctypes.data), "read_segment")
         return el, pt
 
+    def trim_segments(self, from_pos: int) -> None:
+        """keep only positions >= from_pos in the retained segments (what the next shard can reach)"""
+        self._check(self._L.nlzm_mf_trim_segments(self._h, from_pos), "trim_segments")
+
     def drop_segments(self) -> None:
         self._check(self._L.nlzm_mf_drop_segments(self._h), "drop_segments")
 

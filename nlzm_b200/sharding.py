@@ -64,6 +64,13 @@ class ShardedFind:
     def __init__(self, mf, rank: int, world: int, window: int, group=None, transport: str = "ipc"):
         self.mf, self.rank, self.world, self.W, self.group, self.transport = mf, rank, world, window, group, transport
         self.imported_bytes = 0
+        self.ms = {}                  # host wall time per protocol phase, accumulated over run() calls
+
+    def _tick(self, name, t0):
+        import time
+        t1 = time.perf_counter()
+        self.ms[name] = self.ms.get(name, 0.0) + (t1 - t0) * 1e3
+        return t1
 
     def _exchange(self, payload):
         import torch.distributed as dist
@@ -84,12 +91,18 @@ class ShardedFind:
         mf = self.mf
         if self.world == 1:
             return [find(b, e, i) for i, (b, e) in enumerate(blocks)]
+        import time
         first = blocks[0]
         need_from = max(0, first[0] - (self.W - 1))
         err, later, mine = None, [], []
+        t = time.perf_counter()
         try:
             mf.prepare(*first)
+            t = self._tick("prepare", t)
             later = [find(b, e, i + 1) for i, (b, e) in enumerate(blocks[1:])]
+            t = self._tick("later_blocks", t)
+            if self.rank + 1 < self.world:
+                mf.trim_segments(max(0, blocks[-1][1] - (self.W - 1)))     # the next shard reaches no further back
             descs = mf.export_segments()
             for d in descs:
                 mine.append({"desc": bytes(d), "pos": (int(d.pos_begin), int(d.pos_end))})
@@ -99,9 +112,11 @@ class ShardedFind:
                 for i, (d, item) in enumerate(zip(descs, mine)):
                     if item["pos"][1] > nxt - (self.W - 1) - 1:
                         item["host"] = mf.read_segment(i, d)
+            t = self._tick("export", t)
         except Exception as ex:  # noqa: BLE001 - reported to every rank below
             err = f"rank {self.rank}: {ex}"
         everyone = self._exchange({"err": err, "segs": mine})
+        t = self._tick("exchange_wait", t)
         errs = [p["err"] for p in everyone if p["err"]]
         if errs:
             raise RuntimeError("sharded find failed on some rank: " + "; ".join(errs))
@@ -115,14 +130,18 @@ class ShardedFind:
                             mf.import_segment(item["desc"], host_copy=item["host"])
                         else:
                             mf.import_segment(item["desc"], via=1 if self.transport == "ipc" else 0)
-                        self.imported_bytes += (pe - pb) * 64
+                        self.imported_bytes += (pe - pb) * 48
         except Exception as ex:  # noqa: BLE001
             err = f"rank {self.rank}: {ex}"
+        t = self._tick("import", t)
         self._agree(err)               # nobody may recycle a buffer a neighbour is still reading
+        t = self._tick("agree_wait", t)
         try:
             res = find(first[0], first[1], 0)
         except Exception as ex:  # noqa: BLE001
             err = f"rank {self.rank}: {ex}"
             res = None
+        t = self._tick("finish_first", t)
         self._agree(err)
+        self._tick("agree_wait", t)
         return [res] + later
