@@ -311,11 +311,15 @@ def run_ours(args):
     # ---- end-to-end: K steps with HOST buffers through the public calls: set_input (H2D) + submit/fetch (compute +
     #      D2H into pinned memory). The device->host copy of step k runs on the engine's copy stream while step k+1
     #      uploads and computes; every step's result is read on the host inside the timed region.
+    e2e_trace = []
+
     def step_e2e_all(k_steps):
         d2h, pending = 0, None
         for k in range(k_steps):
+            t_a = time.perf_counter()
             rc = mf._L.nlzm_mf_set_input(mf._h, C.c_void_p(x_pin.data_ptr()), total)
             assert rc == 0
+            t_b = time.perf_counter()
 
             def find(b, e, i, k=k):
                 mf.submit(b, e, (k + i) & 1)
@@ -324,10 +328,16 @@ def run_ours(args):
                 slots = [find(b, e, i) for i, (b, e) in enumerate(blocks)]
             else:
                 slots = sf.run(blocks, find)
+            t_c = time.perf_counter()
             if pending is not None:
                 off, st = mf.fetch(pending, copy=False)
                 d2h += off.nbytes + st.nbytes
                 _ = int(off[-1]) + (int(st["len"][-1]) if st.size else 0)
+            t_d = time.perf_counter()
+            sst = mf.stats()
+            e2e_trace.append({"set_input_ms": round((t_b - t_a) * 1e3, 1), "submit_ms": round((t_c - t_b) * 1e3, 1),
+                              "fetch_prev_ms": round((t_d - t_c) * 1e3, 1), "last_find_ms": round(float(sst.ms_total), 1),
+                              "last_d2h_ms": round(float(sst.ms_d2h), 1)})
             if len(slots) == 1:
                 pending = slots[0]
             else:                                            # several blocks per step: drain them in order
@@ -428,7 +438,7 @@ def run_ours(args):
                 "host_phase_ms_rank0": {k: round(v, 2) for k, v in sf.ms.items()},
                 "stage_ms_per_step_rank0": {k: round(v / args.steps, 3) for k, v in acc.items() if k.startswith("ms_")},
                 "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": total * world, "d2h_bytes_per_step": d2h_bytes // max(args.steps, 1),
-                        "ms_per_step": e2e_ms / args.steps,
+                        "ms_per_step": e2e_ms / args.steps, "trace_rank0": e2e_trace[-args.steps:],
                         "path": "per step: nlzm_mf_set_input(pinned host) + nlzm_mf_submit / nlzm_mf_fetch (host view in pinned "
                                 "memory); the copy of step k overlaps the upload + compute of step k+1; wall clock over K steps"},
                 "gpu_launches": all_launches,

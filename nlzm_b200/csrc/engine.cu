@@ -738,28 +738,34 @@ int nlzm_mf::stage_merge(u64 own_b, u64 own_e, Slot &s) {
     CK(cudaMemsetAsync(s.d_offsets.p, 0, (n_own + 1) * 4, st));
     s.n_steps = 0;
     if (nt == 0) return 0;
-    CKI(ensure(keep, (u64)nt * 4)); CKI(ensure(out_idx, (u64)nt * 4));
     CKI(ensure(aux0, (n_own + 1) * 4));
+    const u64 n_bins = (n_own + NLZM_BIN - 1) >> NLZM_BIN_LOG;
+    CKI(ensure(keep, (n_bins + 2) * 4));
     CKI(ensure_prim(nt > n_own + 1 ? nt : n_own + 1));
+    // sort by bin only (the position bits above the bin), finish every bin in shared memory
     int sel = 0;
-    CKI(prim_sort_pairs64(tmp, tk[0].as<u64>(), tk[1].as<u64>(), tv[0].as<u32>(), tv[1].as<u32>(), nt, 0, (int)(9 + bits_for(n_own + 1)), st, &sel));
+    const int lo_bit = 9 + (int)NLZM_BIN_LOG, hi_bit = (int)(9 + bits_for(n_own + 1));
+    if (hi_bit > lo_bit) {
+        CKI(prim_sort_pairs64(tmp, tk[0].as<u64>(), tk[1].as<u64>(), tv[0].as<u32>(), tv[1].as<u32>(), nt, lo_bit, hi_bit, st, &sel));
+    }
     u32 *count = aux0.as<u32>();
     CK(cudaMemsetAsync(count, 0, (n_own + 1) * 4, st));
-    FilterParams fp{tk[sel].as<u64>(), tv[sel].as<u32>(), nt, keep.as<u32>(), count};
-    launch_step_filter(fp, nt, st);
+    BinBoundsParams bb{tk[sel].as<u64>(), nt, keep.as<u32>()};
+    launch_bin_bounds(bb, n_bins + 1, st);
+    Step *staging = (Step *)tk[sel ^ 1].p;                        // the sort's other buffer is free now (8 bytes per tuple >= 6)
+    BinFinishParams fp{tk[sel].as<u64>(), tv[sel].as<u32>(), keep.as<u32>(), (u32)n_own, count, staging};
+    CKI(launch_bin_finish(fp, n_bins, NLZM_BIN_SMEM, st));
     CKI(prim_exclusive_sum(tmp, count, s.d_offsets.as<u32>(), n_own + 1, st));
-    CKI(prim_exclusive_sum(tmp, keep.as<u32>(), out_idx.as<u32>(), nt, st));
     u32 total = 0;
     CK(cudaMemcpyAsync(&total, s.d_offsets.as<u32>() + n_own, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     s.n_steps = total;
     CKI(ensure(s.d_steps, (u64)(total ? total : 1) * sizeof(Step)));
-    CompactParams cp{tk[sel].as<u64>(), tv[sel].as<u32>(), keep.as<u32>(), out_idx.as<u32>(), s.d_steps.as<Step>()};
-    launch_step_compact(cp, nt, st);
+    BinPlaceParams pp{staging, keep.as<u32>(), s.d_offsets.as<u32>(), (u32)n_own, s.d_steps.as<Step>()};
+    CKI(launch_bin_place(pp, n_bins, 0, st));
     return 0;
 }
 
-// all stages for [b, e) into slot s (device buffers); the caller holds `mu`
 int nlzm_mf::compute(u64 b, u64 e, Slot &s) {
     s.begin = b; s.end = e; s.n_steps = 0;
     const u64 n_own = e - b;

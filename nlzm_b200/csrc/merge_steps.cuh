@@ -62,3 +62,142 @@ DEV void step_compact_body(const CompactParams &p, u64 j) {
     p.steps[p.out_idx[j]] = s;
 }
 NLZM_KERNEL_1D(step_compact, CompactParams)
+
+// ================================================================================================
+// Stage M, bin form. The tuples are radix-sorted by BIN only (a bin = 512 consecutive positions: half the
+// key bits, half the sort passes); one CTA then finishes a bin in shared memory: tuples are grouped by
+// position with a counting sort, every position's handful of candidates is ordered and filtered by its own
+// thread, and the surviving steps leave as final 6-byte records, bin-contiguous in a staging array. A
+// global scan of the per-position counts gives the CSR offsets; k_bin_place moves each bin's records to
+// their place (one contiguous copy per bin).
+// ================================================================================================
+#define NLZM_BIN_LOG 9u
+#define NLZM_BIN (1u << NLZM_BIN_LOG)
+#ifdef NLZM_EMU
+#define NLZM_BIN_THREADS 16u                    // the emulation pays for every barrier with host threads
+#else
+#define NLZM_BIN_THREADS 256u
+#endif
+#define NLZM_BIN_CAP 4096u                      // tuples of one pass through shared memory
+#define NLZM_BIN_SMEM (NLZM_BIN_CAP * 8 + NLZM_BIN * 12 + 32)
+
+struct BinBoundsParams { const u64 *keys; u32 nt; u32 *bin_start; };
+DEV void bin_bounds_body(const BinBoundsParams &p, u64 j) {        // j in [0, n_bins]: first tuple of bin j
+    const u64 want = j << (9 + NLZM_BIN_LOG);
+    u32 lo = 0, hi = p.nt;
+    while (lo < hi) { const u32 mid = lo + ((hi - lo) >> 1); if (p.keys[mid] < want) lo = mid + 1; else hi = mid; }
+    p.bin_start[j] = lo;
+}
+NLZM_KERNEL_1D(bin_bounds, BinBoundsParams)
+
+struct BinFinishParams {
+    const u64 *keys; const u32 *dist;     // tuples sorted by bin
+    const u32 *bin_start;                 // n_bins + 1
+    u32 n_own;
+    u32 *count;                           // out: surviving steps per position (n_own + 1, zeroed)
+    Step *staging;                        // out: surviving steps, bin b at staging[bin_start[b] ...)
+};
+
+DEV void bin_finish_cta(const BinFinishParams &p, u32 bid, u32 tid, u8 *smem) {
+    u64 *tup = (u64 *)smem;                                   // len | dist << 9 of the tuples of this pass, grouped by position
+    u32 *cnt = (u32 *)(tup + NLZM_BIN_CAP);                   // tuples per position
+    u32 *off = cnt + NLZM_BIN;                                // start of a position's group inside tup[]
+    u32 *kept = off + NLZM_BIN;                               // surviving steps per position, then their bin-local offsets
+    u32 *sh = kept + NLZM_BIN;                                // [0] = end of this pass's position range, [1] = steps written so far
+    const u32 base = p.bin_start[bid], m = p.bin_start[bid + 1] - base;
+    const u32 pos0 = bid << NLZM_BIN_LOG;
+    const u32 n_pos = (p.n_own - pos0) < NLZM_BIN ? (p.n_own - pos0) : NLZM_BIN;
+    if (m == 0) return;
+    if (tid == 0) sh[1] = 0;
+    u32 lo = 0;
+    while (lo < n_pos) {
+        for (u32 i = tid; i < NLZM_BIN; i += NLZM_BIN_THREADS) { cnt[i] = 0; kept[i] = 0; }
+        NLZM_CTA_SYNC();
+        for (u32 i = tid; i < m; i += NLZM_BIN_THREADS) {
+            const u32 q = (u32)(p.keys[base + i] >> 9) & (NLZM_BIN - 1);
+            if (q >= lo) nlzm_atomic_add(cnt + q, 1u);
+        }
+        NLZM_CTA_SYNC();
+        if (tid == 0) {                                       // positions [lo, hi) whose tuples fit into one pass
+            u32 sum = 0, hi = lo;
+            while (hi < n_pos && (sum + cnt[hi] <= NLZM_BIN_CAP || hi == lo)) { off[hi] = sum; sum += cnt[hi]; ++hi; }
+            sh[0] = hi;
+        }
+        NLZM_CTA_SYNC();
+        const u32 hi = sh[0];
+        for (u32 i = tid; i < NLZM_BIN; i += NLZM_BIN_THREADS) cnt[i] = 0;     // reused as fill counters
+        NLZM_CTA_SYNC();
+        for (u32 i = tid; i < m; i += NLZM_BIN_THREADS) {
+            const u64 k = p.keys[base + i];
+            const u32 q = (u32)(k >> 9) & (NLZM_BIN - 1);
+            if (q >= lo && q < hi) {
+                const u32 slot = off[q] + nlzm_atomic_add(cnt + q, 1u);
+                if (slot < NLZM_BIN_CAP) tup[slot] = (k & 511u) | ((u64)p.dist[base + i] << 9);
+            }
+        }
+        NLZM_CTA_SYNC();
+        // every position: order its candidates by (length descending, distance ascending) and keep the lower
+        // envelope — a candidate survives iff it is nearer than everything at least as long
+        for (u32 q = lo + tid; q < hi; q += NLZM_BIN_THREADS) {
+            u64 *g = tup + off[q];
+            u32 n = cnt[q];
+            if (off[q] + n > NLZM_BIN_CAP) n = NLZM_BIN_CAP - off[q];      // one position beyond a whole pass: cannot happen (<= 264 lengths x 4 finders)
+            for (u32 i = 1; i < n; i++) {                                  // insertion sort, a handful of elements
+                const u64 v = g[i];
+                const u64 kv = ((u64)(511u - (u32)(v & 511u)) << 40) | (v >> 9);
+                u32 j = i;
+                while (j > 0) {
+                    const u64 w = g[j - 1];
+                    const u64 kw = ((u64)(511u - (u32)(w & 511u)) << 40) | (w >> 9);
+                    if (kw <= kv) break;
+                    g[j] = w;
+                    --j;
+                }
+                g[j] = v;
+            }
+            u32 best = 0xFFFFFFFFu, k = 0;
+            for (u32 i = 0; i < n; i++) {
+                const u32 d = (u32)(g[i] >> 9);
+                if (d < best) { best = d; g[k++] = g[i]; }                  // survivors packed at the front, longest first
+            }
+            kept[q] = k;
+            p.count[pos0 + q] = k;
+        }
+        NLZM_CTA_SYNC();
+        if (tid == 0) {                                       // bin-local offsets of the survivors (positions in order)
+            u32 run = sh[1];
+            for (u32 q = lo; q < hi; q++) { const u32 k = kept[q]; kept[q] = run; run += k; }
+            sh[1] = run;
+        }
+        NLZM_CTA_SYNC();
+        for (u32 q = lo + tid; q < hi; q += NLZM_BIN_THREADS) {
+            const u64 *g = tup + off[q];
+            const u32 k = p.count[pos0 + q];
+            Step *out = p.staging + base + kept[q];
+            for (u32 i = 0; i < k; i++) {                     // ascending length = reverse of the kept order
+                const u64 v = g[k - 1 - i];
+                const u32 d = (u32)(v >> 9);
+                Step s;
+                s.dist_lo = (u16)d;
+                s.dist_hi = (u16)((d >> 16) | ((match_min(d) - 2u) << 12));          // bits 12..13: shortest length - 2
+                s.len = (u16)((u32)(v & 511u) | (step_dist_slot(d) << 9));            // bits 9..14: distance slot
+                out[i] = s;
+            }
+        }
+        NLZM_CTA_SYNC();
+        lo = hi;
+    }
+}
+NLZM_KERNEL_CTA_OCC(bin_finish, BinFinishParams, NLZM_BIN_THREADS, 4)
+
+// bin b's records: staging[bin_start[b] ...) -> steps[offsets[first position of b] ...)
+struct BinPlaceParams { const Step *staging; const u32 *bin_start; const u32 *offsets; u32 n_own; Step *steps; };
+DEV void bin_place_cta(const BinPlaceParams &p, u32 bid, u32 tid, u8 *) {
+    const u32 pos0 = bid << NLZM_BIN_LOG;
+    const u32 pos1 = (pos0 + NLZM_BIN) < p.n_own ? (pos0 + NLZM_BIN) : p.n_own;
+    const u32 o0 = p.offsets[pos0], k = p.offsets[pos1] - o0;
+    const u16 *src = (const u16 *)(p.staging + p.bin_start[bid]);
+    u16 *dst = (u16 *)(p.steps + o0);
+    for (u32 i = tid; i < k * 3; i += NLZM_BIN_THREADS) dst[i] = src[i];
+}
+NLZM_KERNEL_CTA(bin_place, BinPlaceParams, NLZM_BIN_THREADS)
