@@ -88,6 +88,13 @@ struct Ev {
 
 static std::string g_create_error;
 
+// Scalars the host needs between stages (counts that size the next launch) are written by a one-thread kernel
+// straight into mapped pinned host memory: a cudaMemcpy would queue behind the previous range's multi-gigabyte
+// device->host copy on the same copy engine and stall the stages for its whole duration.
+#ifndef NLZM_EMU
+__global__ void k_words_to_host(const u32 *src, volatile u32 *dst, u32 n) { for (u32 i = 0; i < n; i++) dst[i] = src[i]; }
+#endif
+
 // device scalars live in one small buffer (u32 slots)
 enum { SC_SUM = 0 /* u64 */, SC_RK_HITS = 8, SC_RK_INTERVALS = 9, SC_RK_VALID = 10 };
 
@@ -159,6 +166,7 @@ struct nlzm_mf {
     DevBuf hblk, sl_k[2], sl_v[2], sl_cnt, sl_off;                 // RK table
     DevBuf hit_k[2], hit_v[2], hit_len, iv, val_k, val_v;          // RK hits / carry intervals
     DevBuf scalars;                                                // misc device scalars
+    u32 *h_words = nullptr, *d_words = nullptr;                    // mapped pinned host memory and its device alias
     PrimTemp tmp;
     DevBuf tmpbuf;
     u32 tuple_cap_mult = 6;
@@ -254,6 +262,21 @@ struct nlzm_mf {
         if (b.p) cudaFree(b.p);
         b.p = nullptr;
         b.bytes = 0;
+    }
+
+    // n 32-bit words at device address `dev` -> host, through the mapped buffer (stream-ordered, then synchronised)
+    int fetch_words(const void *dev, void *host, u32 n) {
+#ifndef NLZM_EMU
+        nlzm_launch_begin("k_words_to_host", st);
+        k_words_to_host<<<1, 1, 0, st>>>((const u32 *)dev, d_words, n);
+        nlzm_launch_end(st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail((int)e, std::string("fetch_words: ") + cudaGetErrorString(e));
+        memcpy(host, h_words, (size_t)n * 4);
+#else
+        memcpy(host, dev, (size_t)n * 4);
+#endif
+        return 0;
     }
 
     int ensure_prim(u64 n) {
@@ -373,8 +396,7 @@ int nlzm_mf::stage_bt4_own(u64 own_b, u64 own_e, u64 u0) {
         if (depth / 2 >= NLZM_MATCH_MAX) break;
         CKI(prim_sum(tmp, act_flag, sum_dev, m, st));
         u64 m_next = 0;
-        CK(cudaMemcpyAsync(&m_next, sum_dev, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        CKI(fetch_words(sum_dev, &m_next, 2));
         if (m_next == 0) break;
         CKI(prim_exclusive_sum(tmp, act_flag, act_idx, m, st));
         RankCompactParams cp{act_flag, act_idx, new_grp, v32[sel].as<u32>(), grp_buf[ab], pos_buf[ab]};
@@ -686,8 +708,7 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     lp.hit_keys = hit_k[0].as<u64>(); lp.hit_vals = hit_v[0].as<u32>(); lp.hit_count = hit_count; lp.hit_cap = (u32)hit_cap;
     launch_rk_lookup(lp, (range + lp.span - 1) / lp.span, st);
     u32 n_hits = 0;
-    CK(cudaMemcpyAsync(&n_hits, hit_count, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CKI(fetch_words(hit_count, &n_hits, 1));
     if (n_hits > hit_cap) {                      // dense hits (e.g. zero runs): redo with room for one hit per position
         rk_all_hits = true;
         rk_overflowed = true;
@@ -706,8 +727,7 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     launch_rk_extend(xp, n_hits, st);
 #endif
     u32 nv = 0;
-    CK(cudaMemcpyAsync(&nv, n_valid, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CKI(fetch_words(n_valid, &nv, 1));
     if (nv == 0) return 0;
     CKI(ensure(val_k, (u64)nv * 8)); CKI(ensure(val_v, (u64)nv * 4));
     int hsel = 0;
@@ -716,8 +736,7 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
                      hit_v[0].as<u32>(), hit_len.as<u32>(), n_valid, iv.as<RkInterval>(), n_iv};
     launch_rk_chain(cp, 1, st);
     u32 niv = 0;
-    CK(cudaMemcpyAsync(&niv, n_iv, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CKI(fetch_words(n_iv, &niv, 1));
     RkExpandParams ex{g, iv.as<RkInterval>(), own_b, own_e, (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
     launch_rk_expand(ex, niv, st);
     return 0;
@@ -729,8 +748,7 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
 int nlzm_mf::stage_merge(u64 own_b, u64 own_e, Slot &s) {
     const u64 n_own = own_e - own_b;
     u32 nt = 0;
-    CK(cudaMemcpyAsync(&nt, tcount.p, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CKI(fetch_words(tcount.p, &nt, 1));
     stats.tuples_last = nt;
     const u32 cap = sink().cap;
     if (nt > cap) return fail(NLZM_MF_E_OVERFLOW, "candidate tuple buffer overflow");
@@ -757,8 +775,7 @@ int nlzm_mf::stage_merge(u64 own_b, u64 own_e, Slot &s) {
     CKI(launch_bin_finish(fp, n_bins, NLZM_BIN_SMEM, st));
     CKI(prim_exclusive_sum(tmp, count, s.d_offsets.as<u32>(), n_own + 1, st));
     u32 total = 0;
-    CK(cudaMemcpyAsync(&total, s.d_offsets.as<u32>() + n_own, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CKI(fetch_words(s.d_offsets.as<u32>() + n_own, &total, 1));
     s.n_steps = total;
     CKI(ensure(s.d_steps, (u64)(total ? total : 1) * sizeof(Step)));
     BinPlaceParams pp{staging, keep.as<u32>(), s.d_offsets.as<u32>(), (u32)n_own, s.d_steps.as<Step>()};
@@ -867,8 +884,7 @@ int nlzm_mf::prepare_impl(u64 b, u64 e) {
         u32 nt = 0;
         if (r == 0) {
             cudaEventRecord(e1, st);
-            CK(cudaMemcpyAsync(&nt, tcount.p, 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            CKI(fetch_words(tcount.p, &nt, 1));
             cudaEventElapsedTime(&stats.ms_prepare, e0, e1);
             if (nt > sink().cap) r = NLZM_MF_E_OVERFLOW;
         }
@@ -879,8 +895,7 @@ int nlzm_mf::prepare_impl(u64 b, u64 e) {
     if (g_prof.on) prof_resolve();
     // the blocks are exported from the retained list; find(b, e) picks them up again as its own universe
     u32 nt = 0;
-    CK(cudaMemcpyAsync(&nt, tcount.p, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CKI(fetch_words(tcount.p, &nt, 1));
     CKI(ensure(prep_tk, (size_t)(nt ? nt : 1) * 8)); CKI(ensure(prep_tv, (size_t)(nt ? nt : 1) * 4));
     if (nt) {
         CK(cudaMemcpyAsync(prep_tk.p, tk[0].p, (size_t)nt * 8, cudaMemcpyDeviceToDevice, st));
@@ -998,6 +1013,14 @@ int nlzm_mf_create(const nlzm_mf_config *cfg, nlzm_mf **out) {
         return NLZM_MF_E_NODEVICE;
     }
 #endif
+#ifndef NLZM_EMU
+    if (cudaHostAlloc((void **)&mf->h_words, 256, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&mf->d_words, mf->h_words, 0) != cudaSuccess) {
+        g_create_error = "cudaHostAlloc(mapped) failed";
+        nlzm_mf_destroy(mf);
+        return NLZM_MF_E_NOMEM;
+    }
+#endif
     int r = mf->ensure(mf->x, cfg->file_len + NLZM_X_PAD + 8);
     if (r == 0) r = mf->ensure(mf->tcount, 64);
     if (r == 0) r = mf->ensure(mf->scalars, 256);
@@ -1036,6 +1059,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
 #ifndef NLZM_EMU
     if (mf->st) cudaStreamDestroy(mf->st);
     if (mf->st_copy) cudaStreamDestroy(mf->st_copy);
+    if (mf->h_words) cudaFreeHost(mf->h_words);
 #endif
     delete mf;
 }

@@ -79,7 +79,7 @@ NLZM_KERNEL_1D(step_compact, CompactParams)
 #define NLZM_BIN_THREADS 256u
 #endif
 #define NLZM_BIN_CAP 4096u                      // tuples of one pass through shared memory
-#define NLZM_BIN_SMEM (NLZM_BIN_CAP * 8 + NLZM_BIN * 12 + 32)
+#define NLZM_BIN_SMEM (NLZM_BIN_CAP * 8 + NLZM_BIN * 12 + (NLZM_BIN_THREADS + 40) * 4)
 
 struct BinBoundsParams { const u64 *keys; u32 nt; u32 *bin_start; };
 DEV void bin_bounds_body(const BinBoundsParams &p, u64 j) {        // j in [0, n_bins]: first tuple of bin j
@@ -98,18 +98,75 @@ struct BinFinishParams {
     Step *staging;                        // out: surviving steps, bin b at staging[bin_start[b] ...)
 };
 
+// exclusive scan of v[0..NLZM_BIN) in place by the whole CTA (NLZM_BIN / threads consecutive entries per thread,
+// thread totals combined through `part`); returns the grand total
+DEV u32 bin_scan(u32 *v, u32 *part, u32 tid) {
+    const u32 per = NLZM_BIN / NLZM_BIN_THREADS;
+    u32 sum = 0;
+    for (u32 i = 0; i < per; i++) sum += v[tid * per + i];
+    part[tid] = sum;
+    NLZM_CTA_SYNC();
+    if (tid < 32) {                                           // one warp scans the thread totals
+        const u32 chunk = NLZM_BIN_THREADS / 32 ? NLZM_BIN_THREADS / 32 : 1;
+        if (tid * chunk < NLZM_BIN_THREADS) {
+            u32 run = 0;
+            for (u32 i = 0; i < chunk && tid * chunk + i < NLZM_BIN_THREADS; i++) { const u32 t = part[tid * chunk + i]; part[tid * chunk + i] = run; run += t; }
+            part[NLZM_BIN_THREADS + tid] = run;
+        }
+    }
+    NLZM_CTA_SYNC();
+    if (tid == 0) {
+        u32 run = 0;
+        const u32 groups = NLZM_BIN_THREADS < 32 ? NLZM_BIN_THREADS : 32;
+        for (u32 g = 0; g < groups; g++) { const u32 t = part[NLZM_BIN_THREADS + g]; part[NLZM_BIN_THREADS + g] = run; run += t; }
+        part[NLZM_BIN_THREADS + 32] = run;
+    }
+    NLZM_CTA_SYNC();
+    {
+        const u32 chunk = NLZM_BIN_THREADS / 32 ? NLZM_BIN_THREADS / 32 : 1;
+        u32 run = part[tid] + part[NLZM_BIN_THREADS + tid / chunk];
+        for (u32 i = 0; i < per; i++) { const u32 t = v[tid * per + i]; v[tid * per + i] = run; run += t; }
+    }
+    NLZM_CTA_SYNC();
+    return part[NLZM_BIN_THREADS + 32];
+}
+
+// order one position's candidates by (length descending, distance ascending) and keep the lower envelope:
+// a candidate survives iff it is nearer than everything at least as long. Survivors end up packed at the
+// front, longest first. g[] holds len | dist << 9.
+DEV u32 bin_envelope(u64 *g, u32 n) {
+    for (u32 i = 1; i < n; i++) {                             // insertion sort, a handful of elements
+        const u64 v = g[i];
+        const u64 kv = ((u64)(511u - (u32)(v & 511u)) << 40) | (v >> 9);
+        u32 j = i;
+        while (j > 0) {
+            const u64 w = g[j - 1];
+            const u64 kw = ((u64)(511u - (u32)(w & 511u)) << 40) | (w >> 9);
+            if (kw <= kv) break;
+            g[j] = w;
+            --j;
+        }
+        g[j] = v;
+    }
+    u32 best = 0xFFFFFFFFu, k = 0;
+    for (u32 i = 0; i < n; i++) {
+        const u32 d = (u32)(g[i] >> 9);
+        if (d < best) { best = d; g[k++] = g[i]; }
+    }
+    return k;
+}
+
 DEV void bin_finish_cta(const BinFinishParams &p, u32 bid, u32 tid, u8 *smem) {
     u64 *tup = (u64 *)smem;                                   // len | dist << 9 of the tuples of this pass, grouped by position
-    u32 *cnt = (u32 *)(tup + NLZM_BIN_CAP);                   // tuples per position
+    u32 *cnt = (u32 *)(tup + NLZM_BIN_CAP);                   // tuples per position, then fill counters
     u32 *off = cnt + NLZM_BIN;                                // start of a position's group inside tup[]
     u32 *kept = off + NLZM_BIN;                               // surviving steps per position, then their bin-local offsets
-    u32 *sh = kept + NLZM_BIN;                                // [0] = end of this pass's position range, [1] = steps written so far
+    u32 *part = kept + NLZM_BIN;                              // scan scratch: NLZM_BIN_THREADS + 33 words
     const u32 base = p.bin_start[bid], m = p.bin_start[bid + 1] - base;
     const u32 pos0 = bid << NLZM_BIN_LOG;
     const u32 n_pos = (p.n_own - pos0) < NLZM_BIN ? (p.n_own - pos0) : NLZM_BIN;
     if (m == 0) return;
-    if (tid == 0) sh[1] = 0;
-    u32 lo = 0;
+    u32 lo = 0, written = 0;
     while (lo < n_pos) {
         for (u32 i = tid; i < NLZM_BIN; i += NLZM_BIN_THREADS) { cnt[i] = 0; kept[i] = 0; }
         NLZM_CTA_SYNC();
@@ -118,14 +175,17 @@ DEV void bin_finish_cta(const BinFinishParams &p, u32 bid, u32 tid, u8 *smem) {
             if (q >= lo) nlzm_atomic_add(cnt + q, 1u);
         }
         NLZM_CTA_SYNC();
-        if (tid == 0) {                                       // positions [lo, hi) whose tuples fit into one pass
-            u32 sum = 0, hi = lo;
-            while (hi < n_pos && (sum + cnt[hi] <= NLZM_BIN_CAP || hi == lo)) { off[hi] = sum; sum += cnt[hi]; ++hi; }
-            sh[0] = hi;
-        }
+        for (u32 i = tid; i < NLZM_BIN; i += NLZM_BIN_THREADS) off[i] = cnt[i];
         NLZM_CTA_SYNC();
-        const u32 hi = sh[0];
-        for (u32 i = tid; i < NLZM_BIN; i += NLZM_BIN_THREADS) cnt[i] = 0;     // reused as fill counters
+        const u32 total = bin_scan(off, part, tid);           // off[q] = tuples of positions [lo, q)
+        // positions [lo, hi) whose tuples fit into one pass: all of them in the common case
+        u32 hi = n_pos;
+        if (total > NLZM_BIN_CAP) {
+            u32 a = lo + 1, b = n_pos;                        // largest hi with off[hi] <= CAP (off is non-decreasing)
+            while (a < b) { const u32 mid = (a + b + 1) >> 1; if ((mid < NLZM_BIN ? off[mid] : total) <= NLZM_BIN_CAP) a = mid; else b = mid - 1; }
+            hi = a;
+        }
+        for (u32 i = tid; i < NLZM_BIN; i += NLZM_BIN_THREADS) cnt[i] = 0;
         NLZM_CTA_SYNC();
         for (u32 i = tid; i < m; i += NLZM_BIN_THREADS) {
             const u64 k = p.keys[base + i];
@@ -136,44 +196,19 @@ DEV void bin_finish_cta(const BinFinishParams &p, u32 bid, u32 tid, u8 *smem) {
             }
         }
         NLZM_CTA_SYNC();
-        // every position: order its candidates by (length descending, distance ascending) and keep the lower
-        // envelope — a candidate survives iff it is nearer than everything at least as long
         for (u32 q = lo + tid; q < hi; q += NLZM_BIN_THREADS) {
-            u64 *g = tup + off[q];
             u32 n = cnt[q];
-            if (off[q] + n > NLZM_BIN_CAP) n = NLZM_BIN_CAP - off[q];      // one position beyond a whole pass: cannot happen (<= 264 lengths x 4 finders)
-            for (u32 i = 1; i < n; i++) {                                  // insertion sort, a handful of elements
-                const u64 v = g[i];
-                const u64 kv = ((u64)(511u - (u32)(v & 511u)) << 40) | (v >> 9);
-                u32 j = i;
-                while (j > 0) {
-                    const u64 w = g[j - 1];
-                    const u64 kw = ((u64)(511u - (u32)(w & 511u)) << 40) | (w >> 9);
-                    if (kw <= kv) break;
-                    g[j] = w;
-                    --j;
-                }
-                g[j] = v;
-            }
-            u32 best = 0xFFFFFFFFu, k = 0;
-            for (u32 i = 0; i < n; i++) {
-                const u32 d = (u32)(g[i] >> 9);
-                if (d < best) { best = d; g[k++] = g[i]; }                  // survivors packed at the front, longest first
-            }
+            if (off[q] + n > NLZM_BIN_CAP) n = off[q] < NLZM_BIN_CAP ? NLZM_BIN_CAP - off[q] : 0;   // a single position beyond a whole pass: cannot happen
+            const u32 k = bin_envelope(tup + off[q], n);
             kept[q] = k;
             p.count[pos0 + q] = k;
         }
         NLZM_CTA_SYNC();
-        if (tid == 0) {                                       // bin-local offsets of the survivors (positions in order)
-            u32 run = sh[1];
-            for (u32 q = lo; q < hi; q++) { const u32 k = kept[q]; kept[q] = run; run += k; }
-            sh[1] = run;
-        }
-        NLZM_CTA_SYNC();
+        const u32 kept_total = bin_scan(kept, part, tid);     // bin-local offsets of the survivors, positions in order
         for (u32 q = lo + tid; q < hi; q += NLZM_BIN_THREADS) {
             const u64 *g = tup + off[q];
             const u32 k = p.count[pos0 + q];
-            Step *out = p.staging + base + kept[q];
+            Step *out = p.staging + base + written + kept[q];
             for (u32 i = 0; i < k; i++) {                     // ascending length = reverse of the kept order
                 const u64 v = g[k - 1 - i];
                 const u32 d = (u32)(v >> 9);
@@ -185,6 +220,7 @@ DEV void bin_finish_cta(const BinFinishParams &p, u32 bid, u32 tid, u8 *smem) {
             }
         }
         NLZM_CTA_SYNC();
+        written += kept_total;
         lo = hi;
     }
 }
