@@ -142,6 +142,7 @@ struct Segment {
     u32 n_elems = 0;     // valid elements (positions past the producing find's range are cut off)
     u64 ptr_pos0 = 0;    // absolute position of bufs->ptr[0]
     u64 pos_b = 0, pos_e = 0;    // absolute positions covered
+    bool imported = false;       // copy of another engine's segment: used by the next find, never exported or kept
     const Elem *elems() const { return bufs->el.as<Elem>() + elem_off; }
     Elem *elems_rw() const { return bufs->el.as<Elem>() + elem_off; }
     const PtrEntry *ptrs() const {       // indexable by (position - u0)
@@ -162,7 +163,7 @@ struct nlzm_mf {
     DevBuf k64[2], v32[2], rank, ptr, aux0, aux1, el[2], part;     // stages S/T
     DevBuf tk[2], tv[2], tcount, keep, out_idx;                    // tuples / merge
     DevBuf e_k[2], e_v[2], e_inv;                                  // BT short-length bucket sort (small windows)
-    DevBuf ht_tab, ht_gmax, ht_coarse, ht_cfirst, ht_clast, ht_ccount, ht_ps, ht_pl, ht_pr;                 // HT: per-tile last-access tables, PS/PL/PR
+    DevBuf ht_snap, ht_tab, ht_gmax, ht_coarse, ht_cfirst, ht_clast, ht_ccount, ht_ps, ht_pl, ht_pr;                 // HT: per-tile last-access tables, PS/PL/PR
     DevBuf hblk, sl_k[2], sl_v[2], sl_cnt, sl_off;                 // RK table
     DevBuf hit_k[2], hit_v[2], hit_len, iv, val_k, val_v;          // RK hits / carry intervals
     DevBuf scalars;                                                // misc device scalars
@@ -338,8 +339,8 @@ bool nlzm_mf::covered_by_segments(u64 b, std::vector<Segment> &use) const {
     const u64 need = b > (u64)(g.W - 1) ? b - (g.W - 1) : 0;
     u64 at = b;
     while (at > need) {
-        const Segment *hit = nullptr;
-        for (const Segment &s : segs) if (s.pos_e == at && s.pos_b < at) { hit = &s; break; }
+        const Segment *hit = nullptr;                  // the longest segment that ends here
+        for (const Segment &s : segs) if (s.pos_e == at && s.pos_b < at && (!hit || s.pos_b < hit->pos_b)) hit = &s;
         if (!hit) return false;
         use.push_back(*hit);
         if (use.size() > max_segments) return false;
@@ -606,7 +607,8 @@ void nlzm_mf::retain_fresh(u64 own_e) {
     fresh.clear();
     const u64 keep_from = own_e > (u64)(g.W - 1) ? own_e - (g.W - 1) : 0;
     std::vector<Segment> kept;
-    for (Segment &sg : segs) if (sg.pos_e > keep_from && (sg.pos_e <= own_e || (prepared && sg.pos_b >= prep_b && sg.pos_e <= prep_e))) kept.push_back(sg);
+    for (Segment &sg : segs)
+        if (!sg.imported && sg.pos_e > keep_from && (sg.pos_e <= own_e || (prepared && sg.pos_b >= prep_b && sg.pos_e <= prep_e))) kept.push_back(sg);
     segs.swap(kept);
     stats.segments_retained = (u32)segs.size();
 }
@@ -657,8 +659,15 @@ int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     sp.n_tiles = (u32)n_tiles; sp.n_groups = (u32)((n_tiles + NLZM_HT_GROUP - 1) / NLZM_HT_GROUP);
     launch_ht_tile_scan(sp, st);
     CKI(launch_ht_prev(tp, n_tiles, nc * 2 + NLZM_HT_STAGE + 16, st));
-    HtFindParams fp{x.as<u8>(), g, c, ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>(), pos0, ht_coarse.as<u32>(), ht_cfirst.as<u32>(), ht_clast.as<u32>(), ht_ccount.as<u32>(), ht_coarse_log, own_b,
-                    (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
+    HtFindParams fp{x.as<u8>(), g, c, ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>(), pos0, ht_coarse.as<u32>(), ht_cfirst.as<u32>(), ht_clast.as<u32>(), ht_ccount.as<u32>(), ht_coarse_log,
+                    nullptr, own_b, (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
+    if (n_coarse) {
+        // what every cell holds at pos0, resolved once per cell over the far prefix
+        CKI(ensure(ht_snap, (nc + 1) * 4));
+        HtSnapParams sn{fp, base_row, ht_snap.as<u32>()};
+        launch_ht_snapshot(sn, nc + 1, st);
+        fp.snap = ht_snap.as<u32>();
+    }
     launch_ht_find(fp, n_acc - own_b, st);
     return 0;
 }
@@ -871,6 +880,11 @@ int nlzm_mf::prepare_impl(u64 b, u64 e) {
     CK(cudaSetDevice(device));
 #endif
     prepared = false;
+    {
+        std::vector<Segment> own_only;                 // imports of an earlier round are stale by definition
+        for (Segment &sg : segs) if (!sg.imported) own_only.push_back(sg);
+        segs.swap(own_only);
+    }
     const u64 n_own = e - b;
     for (int attempt = 0; attempt < 4; attempt++) {
         const u64 cap = n_own * tuple_cap_mult + (1u << 20);
@@ -1052,7 +1066,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
     }
     DevBuf *all[] = {&mf->x, &mf->k64[0], &mf->k64[1], &mf->v32[0], &mf->v32[1], &mf->rank, &mf->ptr, &mf->el[0], &mf->el[1], &mf->part, &mf->aux0,
                      &mf->aux1, &mf->tk[0], &mf->tk[1], &mf->tv[0], &mf->tv[1], &mf->tcount, &mf->keep, &mf->out_idx,
-                     &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->ht_tab, &mf->ht_gmax, &mf->ht_coarse, &mf->ht_cfirst, &mf->ht_clast, &mf->ht_ccount, &mf->ht_ps, &mf->ht_pl, &mf->ht_pr, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
+                     &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->ht_snap, &mf->ht_tab, &mf->ht_gmax, &mf->ht_coarse, &mf->ht_cfirst, &mf->ht_clast, &mf->ht_ccount, &mf->ht_ps, &mf->ht_pl, &mf->ht_pr, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
                      &mf->sl_v[0], &mf->sl_v[1], &mf->sl_cnt, &mf->sl_off, &mf->hit_k[0], &mf->hit_k[1], &mf->hit_v[0],
                      &mf->hit_v[1], &mf->hit_len, &mf->iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf, &mf->prep_tk, &mf->prep_tv};
     for (DevBuf *b : all) mf->release(*b);
@@ -1158,6 +1172,7 @@ int nlzm_mf_export_segments(nlzm_mf *mf, nlzm_mf_segment *out, uint32_t cap, uin
 #endif
     uint32_t i = 0;
     for (const Segment &sg : mf->segs) {
+        if (sg.imported) continue;                     // only what this engine computed itself
         if (out && i < cap) {
             nlzm_mf_segment &d = out[i];
             memset(&d, 0, sizeof d);
@@ -1257,6 +1272,7 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
     sg.ptr_pos0 = d->pos_begin;
     sg.pos_b = d->pos_begin;
     sg.pos_e = d->pos_end;
+    sg.imported = true;
     for (const Segment &o : mf->segs) if (o.pos_b == sg.pos_b && o.pos_e == sg.pos_e) return 0;   // already there
     mf->segs.push_back(sg);
     return 0;
@@ -1267,11 +1283,14 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
 int nlzm_mf_read_segment(nlzm_mf *mf, uint32_t index, void *elems_host, void *ptrs_host) {
     if (!mf || !elems_host || !ptrs_host) return NLZM_MF_E_ARG;
     Turn turn(mf);
-    if (index >= mf->segs.size()) return mf->fail(NLZM_MF_E_ARG, "no such segment");
+    const Segment *found = nullptr;                    // index counts the segments nlzm_mf_export_segments lists
+    uint32_t k = 0;
+    for (const Segment &o : mf->segs) if (!o.imported && k++ == index) { found = &o; break; }
+    if (!found) return mf->fail(NLZM_MF_E_ARG, "no such segment");
 #ifndef NLZM_EMU
     cudaSetDevice(mf->device);
 #endif
-    const Segment &sg = mf->segs[index];
+    const Segment &sg = *found;
     cudaError_t e = cudaMemcpyAsync(elems_host, sg.elems(), (size_t)sg.n_elems * sizeof(Elem), cudaMemcpyDeviceToHost, mf->st);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(ptrs_host, (const u8 *)sg.bufs->ptr.p + (sg.pos_b - sg.ptr_pos0) * sizeof(PtrEntry),

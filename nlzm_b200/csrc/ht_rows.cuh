@@ -38,9 +38,9 @@ struct HtCfg {
 #define NLZM_HT_GROUP 64u                      // tiles per group of the two-level running max
 #define NLZM_HT_TILE (1u << NLZM_HT_TILE_LOG)
 #define NLZM_HT_COARSE_LOG 20u                 // coarse tiles of the far prefix
-#define NLZM_HT_MARGIN 0xFFFFFFFFFFFFull        // PS/PL/PR start this far before the answered range: by default the
-                                               // whole prefix (12 B per position, streaming to build); a smaller margin
-                                               // (option "ht_margin") saves that memory but pays for it in look-ups
+#define NLZM_HT_MARGIN 0ull                    // PS/PL/PR start this far before the answered range (rounded down to a coarse
+                                               // tile): chains that reach further back end in the snapshot of the cells
+                                               // at that point, so the per-position walk does not grow with the prefix
 #define NLZM_HT_THREADS 256
 #define NLZM_HT_STAGE 2048u                     // text bytes staged in shared memory by k_ht_prev
 
@@ -264,6 +264,8 @@ struct HtFindParams {
     const u32 *coarse_last;    // same shape: last access (+1) inside the coarse tile, 0 = none
     const u32 *coarse_count;   // same shape: number of accesses inside the coarse tile
     u32 coarse_log;
+    const u32 *snap;           // raw content of every cell at time pos0 (null when pos0 == 0): a chain that would leave
+                               // [pos0, ..) stops here instead of walking the far prefix
     u64 own_b;
     u32 bt_on;           // exhaustive BT4 runs too: it reports a candidate at least as near and as long for every
                          // match of 4+ bytes, so those need not be queued twice (they would be merged away)
@@ -304,6 +306,8 @@ DEV u32 ht_cell_value(const HtFindParams &p, u32 cell, u64 t, u32 w0, u32 w1) {
             if (geom_epoch(p.g, w) != geom_epoch(p.g, t)) return NLZM_NONE32;  // ... and every ring shift clears it
             return ht_entry(p, w);
         }
+        // nothing wrote this cell since pos0: it still holds what it held then
+        if (p.snap && t >= p.pos0 && (u64)w0 <= p.pos0 && (u64)w1 <= p.pos0) return p.snap[cell];
         if (w0 > w1) return ht_entry(p, w0 - 1);
         const u64 q = w1 - 1;                 // bucket cell-1 accessed at q and pushed the old content of cell-1
         t = q;
@@ -312,6 +316,20 @@ DEV u32 ht_cell_value(const HtFindParams &p, u32 cell, u64 t, u32 w0, u32 w1) {
         w1 = (p.c.rows == 2 && cell > 0) ? ht_pl(p, q, cell) : 0u;
     }
 }
+
+// content of every cell at time pos0, from the coarse tables of the far prefix (one thread per cell; the only
+// place where chains walk the far prefix)
+struct HtSnapParams { HtFindParams f; const u32 *row_at_pos0; u32 *snap_out; };
+DEV void ht_snapshot_body(const HtSnapParams &p, u64 cell64) {
+    const u32 cell = (u32)cell64;
+    const u32 nc = 1u << p.f.c.bits;
+    HtFindParams f = p.f;
+    f.snap = nullptr;
+    const u32 w0 = cell < nc ? p.row_at_pos0[cell] : 0u;
+    const u32 w1 = (f.c.rows == 2 && cell > 0) ? p.row_at_pos0[cell - 1] : 0u;
+    p.snap_out[cell] = ht_cell_value(f, cell, f.pos0, w0, w1);
+}
+NLZM_KERNEL_1D(ht_snapshot, HtSnapParams)
 
 DEV void ht_find_body(const HtFindParams &p, u64 i) {
     const u64 a = p.own_b + i;

@@ -249,3 +249,22 @@ def test_emu_retained_segments_adversarial(emu_lib, orc, kind):
             got, used = _blocks(mf, cuts)
         assert orc.csr_equal(ref, got), (kind, n, orc.first_diff(ref, got))
         assert all(u > 0 for u in used[1:])
+
+
+@pytest.mark.parametrize("kind,hb,clog", [("text", 15, 10), ("mixed", 16, 11), ("zeros_ones", 15, 10), ("period", 15, 12),
+                                          ("longrange", 16, 10)])
+def test_emu_ht_cell_snapshot(emu_lib, orc, kind, hb, clog):
+    """HT2/HT3 of later ranges: per-position data only from the coarse tile before the range on; chains that reach
+    further back end in the snapshot of the cell contents at that point (ring shifts clear cell 0 in between)"""
+    from nlzm_b200 import synth
+    from test_fuzz import _gen
+    from nlzm_b200.matchfinder import MatchFinders
+    n = 140_000
+    x = synth.make(kind, n) if kind in ("text", "mixed", "longrange") else _gen(kind, n, np.random.default_rng(5))
+    for mask in (3, 15):
+        ref = orc.find(x, hb, mask)
+        with MatchFinders(emu_lib) as mf:
+            mf.Init(hb, x, finder_mask=mask)
+            mf.set_option("ht_coarse_log", clog)
+            got, _ = _blocks(mf, [0, 33_000, 71_111, 100_000, n])
+        assert orc.csr_equal(ref, got), (kind, mask, orc.first_diff(ref, got))

@@ -71,3 +71,63 @@ def test_shard_ranges_cover():
             r = [sharding.shard_range(n, i, w) for i in range(w)]
             assert r[0][0] == 0 and r[-1][1] == n
             assert all(r[i][1] == r[i + 1][0] for i in range(w - 1))
+
+
+class _ThreadGroup:
+    """in-process stand-in for the torch.distributed group of ShardedFind: N threads, lock-step exchange"""
+
+    def __init__(self, world):
+        import threading
+        self.world, self.slots, self.bar = world, [None] * world, threading.Barrier(world)
+
+    def exchange(self, rank, payload):
+        self.slots[rank] = payload
+        self.bar.wait()
+        out = list(self.slots)
+        self.bar.wait()
+        return out
+
+
+@pytest.mark.parametrize("world,hb,steps", [(8, 16, 2), (4, 15, 2), (3, 16, 1)])
+def test_sharded_find_many_ranks_in_process(emu_lib, orc, world, hb, steps):
+    """the bench's protocol (ShardedFind) with 3..8 ranks whose shards are SMALLER than the window (a range then
+    needs the segments of two or three ranks behind it, as C3 on 8 GPUs does), repeated for several steps on the
+    same engines; ranks are threads, engines are emulated, segments travel as in-process copies"""
+    import threading
+    from nlzm_b200 import synth, sharding
+    from nlzm_b200.matchfinder import MatchFinders
+    x = synth.longrange(200_000, 17)
+    W = 1 << hb
+    ref = orc.find(x, hb, orc.F_ALL)
+    grp = _ThreadGroup(world)
+    results, errors = [None] * world, []
+
+    def rank_main(rank):
+        try:
+            b, e = sharding.shard_range(x.size, rank, world)
+            with MatchFinders(emu_lib) as mf:
+                mf.Init(hb, x)
+                sf = sharding.ShardedFind(mf, rank, world, W, group=None, transport="peer")
+                sf._exchange = lambda payload: grp.exchange(rank, payload)
+                blocks = sharding.blocks_for(b, e, W, max_block=1 << 28)
+                for _ in range(steps):
+                    mine = []
+
+                    def find(bb, ee, i):
+                        off, st = mf.FindAndUpdate(bb, ee, slot=i & 1)
+                        mine.append((bb, ee, off, st))
+                    sf.run(blocks, find)
+                    grp.bar.wait()                       # a step ends everywhere before the next one starts
+                results[rank] = mine
+        except Exception as ex:  # noqa: BLE001
+            errors.append((rank, repr(ex)))
+            grp.bar.abort()
+
+    th = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    got = sharding.concat_views([p for r in results for p in r])
+    assert orc.csr_equal(ref, got), orc.first_diff(ref, got)
