@@ -660,12 +660,16 @@ int nlzm_mf::stage_ht(u64 own_b, u64 own_e, const HtCfg &c) {
     launch_ht_tile_scan(sp, st);
     CKI(launch_ht_prev(tp, n_tiles, nc * 2 + NLZM_HT_STAGE + 16, st));
     HtFindParams fp{x.as<u8>(), g, c, ht_ps.as<u32>(), ht_pl.as<u32>(), ht_pr.as<u32>(), pos0, ht_coarse.as<u32>(), ht_cfirst.as<u32>(), ht_clast.as<u32>(), ht_ccount.as<u32>(), ht_coarse_log,
-                    nullptr, own_b, (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
+                    0u, nullptr, own_b, (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
     if (n_coarse) {
         // what every cell holds at pos0, resolved once per cell over the far prefix
         CKI(ensure(ht_snap, (nc + 1) * 4));
         HtSnapParams sn{fp, base_row, ht_snap.as<u32>()};
+#ifndef NLZM_EMU
+        launch_ht_snapshot(sn, (nc + 1) * 32, st);           // one warp per cell
+#else
         launch_ht_snapshot(sn, nc + 1, st);
+#endif
         fp.snap = ht_snap.as<u32>();
     }
     launch_ht_find(fp, n_acc - own_b, st);

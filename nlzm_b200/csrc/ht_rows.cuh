@@ -37,7 +37,7 @@ struct HtCfg {
 #define NLZM_HT_TILE_LOG 15u                   // fine tiles: k_ht_prev walks these in order (in-tile offsets fit u16)
 #define NLZM_HT_GROUP 64u                      // tiles per group of the two-level running max
 #define NLZM_HT_TILE (1u << NLZM_HT_TILE_LOG)
-#define NLZM_HT_COARSE_LOG 20u                 // coarse tiles of the far prefix
+#define NLZM_HT_COARSE_LOG 17u                 // coarse tiles of the far prefix
 #define NLZM_HT_MARGIN 0ull                    // PS/PL/PR start this far before the answered range (rounded down to a coarse
                                                // tile): chains that reach further back end in the snapshot of the cells
                                                // at that point, so the per-position walk does not grow with the prefix
@@ -264,6 +264,7 @@ struct HtFindParams {
     const u32 *coarse_last;    // same shape: last access (+1) inside the coarse tile, 0 = none
     const u32 *coarse_count;   // same shape: number of accesses inside the coarse tile
     u32 coarse_log;
+    u32 warp_scan;             // 1: all lanes of a warp run the same chain (snapshot kernel) and scan together
     const u32 *snap;           // raw content of every cell at time pos0 (null when pos0 == 0): a chain that would leave
                                // [pos0, ..) stops here instead of walking the far prefix
     u64 own_b;
@@ -289,6 +290,22 @@ DEV u32 ht_last_before(const HtFindParams &p, u32 bucket, u64 q) {
     if ((u64)last - 1 < q) return last;                                 // the tile's last access lies before q
     if (p.coarse_count[cell] == 2) return first;                        // first < q <= last and nothing in between
     const u32 shift = 32 - p.c.bits;                                    // three or more accesses around q: scan back
+#if !defined(NLZM_EMU) && defined(__CUDA_ARCH__)
+    if (p.warp_scan) {
+        // snapshot kernel: the 32 lanes of a warp follow the same chain, so the scan is theirs together —
+        // 32 positions per step, coalesced, the nearest hit picked with a ballot
+        const u32 lane = threadIdx.x & 31;
+        for (u64 hi = q; hi > t0; hi = hi >= 32 ? hi - 32 : 0) {
+            const u64 a = hi - 1 - lane;                                    // hi-1, hi-2, ... (wraps below 0: masked)
+            const bool in = hi > lane && a >= t0;
+            const bool hit = in && (ht_hash(p.x, a, p.c.nbytes) >> shift) == bucket;
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+            if (m) return (u32)(hi - 1 - (u32)(__ffs((int)m) - 1)) + 1u;
+            if (hi < 32) break;
+        }
+        return p.coarse[cell];
+    }
+#endif
     for (u64 a = q; a-- > t0; )
         if ((ht_hash(p.x, a, p.c.nbytes) >> shift) == bucket) return (u32)a + 1u;
     return p.coarse[cell];
@@ -320,14 +337,25 @@ DEV u32 ht_cell_value(const HtFindParams &p, u32 cell, u64 t, u32 w0, u32 w1) {
 // content of every cell at time pos0, from the coarse tables of the far prefix (one thread per cell; the only
 // place where chains walk the far prefix)
 struct HtSnapParams { HtFindParams f; const u32 *row_at_pos0; u32 *snap_out; };
-DEV void ht_snapshot_body(const HtSnapParams &p, u64 cell64) {
-    const u32 cell = (u32)cell64;
+DEV void ht_snapshot_body(const HtSnapParams &p, u64 i) {
+#if !defined(NLZM_EMU) && defined(__CUDA_ARCH__)
+    const u32 cell = (u32)(i >> 5);                                      // one warp per cell
+#else
+    const u32 cell = (u32)i;
+#endif
     const u32 nc = 1u << p.f.c.bits;
     HtFindParams f = p.f;
     f.snap = nullptr;
+#if !defined(NLZM_EMU) && defined(__CUDA_ARCH__)
+    f.warp_scan = 1;
+#endif
     const u32 w0 = cell < nc ? p.row_at_pos0[cell] : 0u;
     const u32 w1 = (f.c.rows == 2 && cell > 0) ? p.row_at_pos0[cell - 1] : 0u;
-    p.snap_out[cell] = ht_cell_value(f, cell, f.pos0, w0, w1);
+    const u32 v = ht_cell_value(f, cell, f.pos0, w0, w1);
+#if !defined(NLZM_EMU) && defined(__CUDA_ARCH__)
+    if ((threadIdx.x & 31) == 0)
+#endif
+    p.snap_out[cell] = v;
 }
 NLZM_KERNEL_1D(ht_snapshot, HtSnapParams)
 
