@@ -498,6 +498,9 @@ def run_c3(args, torch, dist, dev, local, rank, world, gloo, replicate, barrier,
     per_rank.update({k: round(v / steps_timed, 2) for k, v in acc.items() if k.startswith("ms_")})
     per_rank["segments_queried"] = acc.get("segments_queried", 0) // steps_timed
     per_rank["host_phase_ms"] = {k: round(v / (steps_timed + 1), 2) for k, v in sf.ms.items()}
+    lst = mf.stats()
+    per_rank["last_import"] = {"ms": round(float(lst.ms_import), 2), "bytes": int(lst.bytes_imported),
+                               "GBps": round(lst.bytes_imported / max(lst.ms_import, 1e-3) / 1e6, 1)}
     t = torch.tensor([wall_ms], dtype=torch.float64, device=dev)
     allr = [per_rank]
     if world > 1:

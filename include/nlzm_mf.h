@@ -105,6 +105,9 @@ typedef struct {
     float ms_prepare;              /* last nlzm_mf_prepare (also counted in the ms_total of the find that continues it) */
     uint32_t segments_queried;     /* last find: retained / imported segments its first block looked into */
     uint32_t segments_retained;    /* segments kept after the last find */
+    float ms_import;               /* device time of the segment copies since the last nlzm_mf_prepare (CUDA events) */
+    uint32_t reserved;
+    uint64_t bytes_imported;       /* ... and their size */
 } nlzm_mf_stats;
 
 int nlzm_mf_abi_version(void);

@@ -34,7 +34,8 @@ class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("tuples_last", C.c_uint64)] + \
                [(n, C.c_float) for n in ("ms_rank", "ms_levels", "ms_ht", "ms_rk", "ms_merge", "ms_total", "ms_d2h",
                                           "ms_cross", "ms_prepare")] + \
-               [("segments_queried", C.c_uint32), ("segments_retained", C.c_uint32)]
+               [("segments_queried", C.c_uint32), ("segments_retained", C.c_uint32), ("ms_import", C.c_float),
+                ("reserved", C.c_uint32), ("bytes_imported", C.c_uint64)]
 
 
 class SegmentDesc(C.Structure):

@@ -884,6 +884,8 @@ int nlzm_mf::prepare_impl(u64 b, u64 e) {
     CK(cudaSetDevice(device));
 #endif
     prepared = false;
+    stats.ms_import = 0;
+    stats.bytes_imported = 0;
     {
         std::vector<Segment> own_only;                 // imports of an earlier round are stale by definition
         for (Segment &sg : segs) if (!sg.imported) own_only.push_back(sg);
@@ -1258,9 +1260,26 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
         src_el = (const u8 *)open_el;
         src_ptr = (const u8 *)open_ptr;
     }
-    cudaError_t e = cudaMemcpyPeerAsync(bufs->el.p, mf->device, src_el + d->elems_offset_bytes, via_ipc ? mf->device : d->device, (size_t)d->elems_bytes, mf->st);
-    if (e == cudaSuccess) e = cudaMemcpyPeerAsync(bufs->ptr.p, mf->device, src_ptr + d->ptrs_offset_bytes, via_ipc ? mf->device : d->device, (size_t)d->ptrs_bytes, mf->st);
+    Ev c0, c1;
+    cudaEventRecord(c0, mf->st);
+    cudaError_t e;
+    if (via_ipc) {
+        // an IPC mapping is an ordinary device pointer of this process (unified addressing finds the owner GPU)
+        e = cudaMemcpyAsync(bufs->el.p, src_el + d->elems_offset_bytes, (size_t)d->elems_bytes, cudaMemcpyDefault, mf->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(bufs->ptr.p, src_ptr + d->ptrs_offset_bytes, (size_t)d->ptrs_bytes, cudaMemcpyDefault, mf->st);
+    } else {
+        e = cudaMemcpyPeerAsync(bufs->el.p, mf->device, src_el + d->elems_offset_bytes, d->device, (size_t)d->elems_bytes, mf->st);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(bufs->ptr.p, mf->device, src_ptr + d->ptrs_offset_bytes, d->device, (size_t)d->ptrs_bytes, mf->st);
+    }
+    cudaEventRecord(c1, mf->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
+    if (e == cudaSuccess) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c0, c1);
+        std::lock_guard<std::mutex> l(mf->stats_mu);
+        mf->stats.ms_import += ms;
+        mf->stats.bytes_imported += d->elems_bytes + d->ptrs_bytes;
+    }
     if (e != cudaSuccess) return mf->fail((int)e, std::string("segment copy: ") + cudaGetErrorString(e));
 #else
     (void)via_ipc;

@@ -64,6 +64,7 @@ class ShardedFind:
     def __init__(self, mf, rank: int, world: int, window: int, group=None, transport: str = "ipc"):
         self.mf, self.rank, self.world, self.W, self.group, self.transport = mf, rank, world, window, group, transport
         self.imported_bytes = 0
+        self._fast = transport != "host"  # tensor collectives (tests that replace _exchange switch this off)
         self.ms = {}                  # host wall time per protocol phase, accumulated over run() calls
 
     def _tick(self, name, t0):
@@ -77,6 +78,48 @@ class ShardedFind:
         out = [None] * self.world
         dist.all_gather_object(out, payload, group=self.group)
         return out
+
+    MAX_SEGS = 12
+
+    def _exchange_descs(self, err, mine):
+        """descriptors of every rank in ONE fixed-size all_gather (a few KB over the host-side group);
+        falls back to the object exchange when there is an error text or a host copy to ship"""
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from ._lib import SegmentDesc
+        self.DESC_BYTES = ctypes.sizeof(SegmentDesc)
+        slow = err is not None or any("host" in m for m in mine) or len(mine) > self.MAX_SEGS
+        rec = 8 + self.MAX_SEGS * self.DESC_BYTES
+        buf = torch.zeros(rec, dtype=torch.uint8)
+        buf[0] = 1 if slow else 0
+        if not slow:
+            buf[1] = len(mine)
+            for i, m in enumerate(mine):
+                assert len(m["desc"]) == self.DESC_BYTES
+                buf[8 + i * self.DESC_BYTES: 8 + (i + 1) * self.DESC_BYTES] = torch.frombuffer(bytearray(m["desc"]), dtype=torch.uint8)
+        allb = [torch.empty(rec, dtype=torch.uint8) for _ in range(self.world)]
+        dist.all_gather(allb, buf, group=self.group)
+        if any(int(b[0]) for b in allb):                 # somebody needs the general path: everybody takes it
+            return self._exchange({"err": err, "segs": mine})
+        out = []
+        for b in allb:
+            segs = []
+            for i in range(int(b[1])):
+                raw = bytes(b[8 + i * self.DESC_BYTES: 8 + (i + 1) * self.DESC_BYTES].numpy())
+                d = SegmentDesc.from_buffer_copy(raw)
+                segs.append({"desc": raw, "pos": (int(d.pos_begin), int(d.pos_end))})
+            out.append({"err": None, "segs": segs})
+        return out
+
+    def _agree_fast(self, err):
+        """one small all_reduce; the error texts are only exchanged when there is an error somewhere"""
+        import torch
+        import torch.distributed as dist
+        flag = torch.tensor([1 if err else 0], dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        if int(flag.item()):
+            self._agree(err)
 
     def _agree(self, err):
         """every rank learns whether any rank failed in the phase just finished (also a barrier)"""
@@ -115,7 +158,7 @@ class ShardedFind:
             t = self._tick("export", t)
         except Exception as ex:  # noqa: BLE001 - reported to every rank below
             err = f"rank {self.rank}: {ex}"
-        everyone = self._exchange({"err": err, "segs": mine})
+        everyone = self._exchange_descs(err, mine) if self._fast else self._exchange({"err": err, "segs": mine})
         t = self._tick("exchange_wait", t)
         errs = [p["err"] for p in everyone if p["err"]]
         if errs:
@@ -134,7 +177,7 @@ class ShardedFind:
         except Exception as ex:  # noqa: BLE001
             err = f"rank {self.rank}: {ex}"
         t = self._tick("import", t)
-        self._agree(err)               # nobody may recycle a buffer a neighbour is still reading
+        (self._agree_fast if self._fast else self._agree)(err)     # nobody may recycle a buffer a neighbour is still reading
         t = self._tick("agree_wait", t)
         try:
             res = find(first[0], first[1], 0)
@@ -142,6 +185,6 @@ class ShardedFind:
             err = f"rank {self.rank}: {ex}"
             res = None
         t = self._tick("finish_first", t)
-        self._agree(err)
+        (self._agree_fast if self._fast else self._agree)(err)
         self._tick("agree_wait", t)
         return [res] + later

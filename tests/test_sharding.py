@@ -35,6 +35,13 @@ def _worker(rank, world, port, q):
             off, st = mf.FindAndUpdate(bb, ee, slot=i & 1)
             mine.append((bb, ee, off, st, int(mf.stats().segments_queried)))
         sf.run(blocks, find)
+        # the fixed-size descriptor exchange of the GPU transports carries the same information as the object path
+        descs = [{"desc": bytes(d), "pos": (int(d.pos_begin), int(d.pos_end))} for d in mf.export_segments()]
+        fast = sharding.ShardedFind(mf, rank, world, 1 << 15, group=None, transport="ipc")._exchange_descs(None, descs)
+        slow = sf._exchange({"err": None, "segs": descs})
+        assert [[s["pos"] for s in r["segs"]] for r in fast] == [[s["pos"] for s in r["segs"]] for r in slow]
+        assert [[s["desc"] for s in r["segs"]] for r in fast] == [[s["desc"] for s in r["segs"]] for r in slow]
+        sharding.ShardedFind(mf, rank, world, 1 << 15, group=None, transport="ipc")._agree_fast(None)
     assert all(u > 0 for (bb, _, _, _, u) in mine if bb > 0), [m[4] for m in mine]
     parts = [None] * world
     dist.gather_object([m[:4] for m in mine], parts if rank == 0 else None, dst=0)
@@ -109,6 +116,7 @@ def test_sharded_find_many_ranks_in_process(emu_lib, orc, world, hb, steps):
                 mf.Init(hb, x)
                 sf = sharding.ShardedFind(mf, rank, world, W, group=None, transport="peer")
                 sf._exchange = lambda payload: grp.exchange(rank, payload)
+                sf._fast = False
                 blocks = sharding.blocks_for(b, e, W, max_block=1 << 28)
                 for _ in range(steps):
                     mine = []
