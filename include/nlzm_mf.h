@@ -138,7 +138,8 @@ int nlzm_mf_get_stats(const nlzm_mf *mf, nlzm_mf_stats *out);
  *
  * Position sharding across GPUs (the input is replicated, each engine owns a range):
  *   1. every engine:  nlzm_mf_prepare(own_begin, own_end)      rank + merge its own range only
- *   2. every engine:  nlzm_mf_export_segments(...)              descriptors (device pointers + CUDA IPC handles)
+ *   2. every engine:  nlzm_mf_export_segments(...)              descriptors (device pointers; same process), or
+ *                     nlzm_mf_publish_segments(...)             copies in the engine's export buffer + its CUDA IPC handle
  *   3. engine r:      nlzm_mf_import_segment(...) for the segments of the ranges behind own_begin that lie
  *                     within the window (copied over NVLink: peer copy in one process, CUDA IPC across processes)
  *   4. engine r:      nlzm_mf_find(own_begin, own_end, ...)     continues from step 1
@@ -158,6 +159,10 @@ int nlzm_mf_prepare(nlzm_mf *mf, uint64_t begin, uint64_t end);
 int nlzm_mf_export_segments(nlzm_mf *mf, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out);
 /* via: 0 = elems_alloc / ptrs_alloc are device pointers of this process (peer copy), 1 = open the IPC handles,
  *      2 = elems_alloc / ptrs_alloc are HOST copies of the two slices made with nlzm_mf_read_segment */
+/* Export for OTHER PROCESSES: copies this engine's own segments, cut down to positions >= from_pos, into one export
+ * buffer that lives as long as the engine and describes the copies (call with out == NULL to get the count). The
+ * descriptors carry the CUDA IPC handle of that buffer: an importer maps it once, however often it is refilled. */
+int nlzm_mf_publish_segments(nlzm_mf *mf, uint64_t from_pos, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out);
 int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *seg, int via);
 int nlzm_mf_read_segment(nlzm_mf *mf, uint32_t index, void *elems_host, void *ptrs_host);
 int nlzm_mf_drop_segments(nlzm_mf *mf);

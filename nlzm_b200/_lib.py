@@ -52,7 +52,7 @@ class KernelTime(C.Structure):
 EXPORTS = ["nlzm_mf_set_option", "nlzm_mf_profile", "nlzm_mf_get_kernel_times", "nlzm_mf_abi_version", "nlzm_mf_get_geometry", "nlzm_mf_create", "nlzm_mf_destroy",
            "nlzm_mf_last_error", "nlzm_mf_set_input", "nlzm_mf_set_input_device", "nlzm_mf_find",
            "nlzm_mf_find_device", "nlzm_mf_submit", "nlzm_mf_fetch", "nlzm_mf_get_stats",
-           "nlzm_mf_prepare", "nlzm_mf_export_segments", "nlzm_mf_import_segment", "nlzm_mf_drop_segments", "nlzm_mf_read_segment", "nlzm_mf_trim_segments"]
+           "nlzm_mf_prepare", "nlzm_mf_export_segments", "nlzm_mf_import_segment", "nlzm_mf_drop_segments", "nlzm_mf_read_segment", "nlzm_mf_trim_segments", "nlzm_mf_publish_segments"]
 
 
 def bind_prototypes(L):
@@ -75,6 +75,7 @@ def bind_prototypes(L):
     L.nlzm_mf_export_segments.argtypes = [C.c_void_p, C.POINTER(SegmentDesc), C.c_uint32, C.POINTER(C.c_uint32)]
     L.nlzm_mf_import_segment.argtypes = [C.c_void_p, C.POINTER(SegmentDesc), C.c_int]
     L.nlzm_mf_drop_segments.argtypes = [C.c_void_p]
+    L.nlzm_mf_publish_segments.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(SegmentDesc), C.c_uint32, C.POINTER(C.c_uint32)]
     L.nlzm_mf_trim_segments.argtypes = [C.c_void_p, C.c_uint64]
     L.nlzm_mf_read_segment.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.nlzm_mf_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]

@@ -304,6 +304,9 @@ struct nlzm_mf {
     void retain_fresh(u64 own_e);
     void add_segments(const std::vector<Segment> &v);
     int trim_segments(u64 from);
+    int publish_segments(u64 from, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out);
+    DevBuf xstage;                         // export buffer: ONE allocation (one IPC handle, opened once by every importer)
+                                           // that holds the published copies of this engine's segments
     int stage_ht(u64 own_b, u64 own_e, const HtCfg &c);
     int stage_rk(u64 own_b, u64 own_e);
     int stage_merge(u64 own_b, u64 own_e, Slot &s);
@@ -597,6 +600,77 @@ int nlzm_mf::trim_segments(u64 from) {
     }
     segs.swap(kept);
     stats.segments_retained = (u32)segs.size();
+    return 0;
+}
+
+// Copies of this engine's own segments, cut down to positions >= from, into the export buffer, and their
+// descriptors. Importers in other processes map that one allocation once; what changes from round to round is
+// only its content. (Handing out the level-array buffers themselves would mean a new IPC mapping on the importing
+// side whenever the buffers rotate: hundreds of milliseconds for allocations of several gigabytes.)
+int nlzm_mf::publish_segments(u64 from, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out) {
+    struct Plan { const Segment *sg; u64 first, n_keep, el_off, pt_off; };
+    std::vector<Plan> plan;
+    u64 bytes = 0;
+    for (const Segment &sg : segs) {
+        if (sg.imported || sg.pos_e <= from) continue;
+        Plan pl;
+        pl.sg = &sg;
+        pl.first = sg.pos_b > from ? sg.pos_b : from;
+        pl.n_keep = sg.pos_e - pl.first;                       // one element per position
+        pl.el_off = bytes; bytes += (pl.n_keep * sizeof(Elem) + 255) & ~255ull;
+        pl.pt_off = bytes; bytes += (pl.n_keep * sizeof(PtrEntry) + 255) & ~255ull;
+        plan.push_back(pl);
+    }
+    *n_out = (uint32_t)plan.size();
+    if (!out || cap < plan.size()) return 0;
+    if (bytes > xstage.bytes) { ipc_made.erase(xstage.p); CKI(ensure(xstage, bytes + (bytes >> 3))); }
+    u8 *base = xstage.as<u8>();
+    for (const Plan &pl : plan) {
+        const Segment &sg = *pl.sg;
+        if (pl.first == sg.pos_b) {
+            CK(cudaMemcpyAsync(base + pl.el_off, sg.elems(), pl.n_keep * sizeof(Elem), cudaMemcpyDeviceToDevice, st));
+        } else {
+            const u64 n = sg.n_elems;
+            CKI(ensure(aux0, n * 4)); CKI(ensure(aux1, n * 4));
+            CKI(ensure_prim(n));
+            SegTrimParams tp{sg.elems(), (Elem *)(base + pl.el_off), aux0.as<u32>(), aux1.as<u32>(), (u32)(pl.first - sg.u0)};
+            launch_seg_trim_flag(tp, n, st);
+            CKI(prim_exclusive_sum(tmp, aux0.as<u32>(), aux1.as<u32>(), n, st));
+            launch_seg_trim_move(tp, n, st);
+        }
+        CK(cudaMemcpyAsync(base + pl.pt_off, (const u8 *)sg.bufs->ptr.p + (pl.first - sg.ptr_pos0) * sizeof(PtrEntry),
+                           pl.n_keep * sizeof(PtrEntry), cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    std::string handle;
+#ifndef NLZM_EMU
+    {
+        auto it = ipc_made.find(xstage.p);
+        if (it == ipc_made.end()) {
+            cudaIpcMemHandle_t h;
+            if (cudaIpcGetMemHandle(&h, xstage.p) == cudaSuccess) it = ipc_made.emplace(xstage.p, std::string((const char *)&h, sizeof h)).first;
+            else cudaGetLastError();
+        }
+        if (it != ipc_made.end()) handle = it->second;
+    }
+#endif
+    for (size_t i = 0; i < plan.size(); i++) {
+        const Plan &pl = plan[i];
+        nlzm_mf_segment &d = out[i];
+        memset(&d, 0, sizeof d);
+        d.pos_begin = pl.first;
+        d.pos_end = pl.sg->pos_e;
+        d.origin = pl.sg->u0;
+        d.n_elems = pl.n_keep;
+        d.elems_offset_bytes = pl.el_off;
+        d.elems_bytes = pl.n_keep * sizeof(Elem);
+        d.ptrs_offset_bytes = pl.pt_off;
+        d.ptrs_bytes = pl.n_keep * sizeof(PtrEntry);
+        d.elems_alloc = xstage.p;
+        d.ptrs_alloc = xstage.p;
+        d.device = device;
+        if (!handle.empty()) { memcpy(d.ipc_elems, handle.data(), handle.size()); memcpy(d.ipc_ptrs, handle.data(), handle.size()); d.flags = 3u; }
+    }
     return 0;
 }
 
@@ -1074,7 +1148,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
                      &mf->aux1, &mf->tk[0], &mf->tk[1], &mf->tv[0], &mf->tv[1], &mf->tcount, &mf->keep, &mf->out_idx,
                      &mf->e_k[0], &mf->e_k[1], &mf->e_v[0], &mf->e_v[1], &mf->e_inv, &mf->ht_snap, &mf->ht_tab, &mf->ht_gmax, &mf->ht_coarse, &mf->ht_cfirst, &mf->ht_clast, &mf->ht_ccount, &mf->ht_ps, &mf->ht_pl, &mf->ht_pr, &mf->hblk, &mf->sl_k[0], &mf->sl_k[1],
                      &mf->sl_v[0], &mf->sl_v[1], &mf->sl_cnt, &mf->sl_off, &mf->hit_k[0], &mf->hit_k[1], &mf->hit_v[0],
-                     &mf->hit_v[1], &mf->hit_len, &mf->iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf, &mf->prep_tk, &mf->prep_tv};
+                     &mf->hit_v[1], &mf->hit_len, &mf->iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf, &mf->prep_tk, &mf->prep_tv, &mf->xstage};
     for (DevBuf *b : all) mf->release(*b);
 #ifndef NLZM_EMU
     if (mf->st) cudaStreamDestroy(mf->st);
@@ -1330,6 +1404,15 @@ int nlzm_mf_trim_segments(nlzm_mf *mf, uint64_t from_pos) {
     cudaSetDevice(mf->device);
 #endif
     return mf->trim_segments(from_pos);
+}
+
+int nlzm_mf_publish_segments(nlzm_mf *mf, uint64_t from_pos, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out) {
+    if (!mf || !n_out) return NLZM_MF_E_ARG;
+    Turn turn(mf);
+#ifndef NLZM_EMU
+    cudaSetDevice(mf->device);
+#endif
+    return mf->publish_segments(from_pos, out, cap, n_out);
 }
 
 int nlzm_mf_drop_segments(nlzm_mf *mf) {

@@ -109,6 +109,14 @@ class MatchFinders:
         self._check(self._L.nlzm_mf_export_segments(self._h, arr, n.value, C.byref(n)), "export_segments")
         return [arr[i] for i in range(n.value)]
 
+    def publish_segments(self, from_pos: int) -> list:
+        """copies of the own segments at positions >= from_pos in the engine's export buffer (one IPC handle)"""
+        n = C.c_uint32(0)
+        self._check(self._L.nlzm_mf_publish_segments(self._h, from_pos, None, 0, C.byref(n)), "publish_segments")
+        arr = (_lib.SegmentDesc * max(n.value, 1))()
+        self._check(self._L.nlzm_mf_publish_segments(self._h, from_pos, arr, n.value, C.byref(n)), "publish_segments")
+        return [arr[i] for i in range(n.value)]
+
     def import_segment(self, desc, via: int = 0, host_copy=None) -> None:
         """desc: a SegmentDesc from export_segments() of another engine, or its bytes (from another process).
         via 0: same process (peer copy), 1: CUDA IPC handles, 2: host_copy = (elems, ptrs) numpy byte arrays"""

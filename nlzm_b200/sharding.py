@@ -144,9 +144,13 @@ class ShardedFind:
             t = self._tick("prepare", t)
             later = [find(b, e, i + 1) for i, (b, e) in enumerate(blocks[1:])]
             t = self._tick("later_blocks", t)
-            if self.rank + 1 < self.world:
-                mf.trim_segments(max(0, blocks[-1][1] - (self.W - 1)))     # the next shard reaches no further back
-            descs = mf.export_segments()
+            reach = max(0, blocks[-1][1] - (self.W - 1))              # the next shard reaches no further back
+            if self.transport == "ipc":
+                descs = mf.publish_segments(reach) if self.rank + 1 < self.world else []
+            else:
+                if self.rank + 1 < self.world:
+                    mf.trim_segments(reach)
+                descs = mf.export_segments()
             for d in descs:
                 mine.append({"desc": bytes(d), "pos": (int(d.pos_begin), int(d.pos_end))})
             if self.transport == "host":

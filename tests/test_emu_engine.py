@@ -268,3 +268,37 @@ def test_emu_ht_cell_snapshot(emu_lib, orc, kind, hb, clog):
             mf.set_option("ht_coarse_log", clog)
             got, _ = _blocks(mf, [0, 33_000, 71_111, 100_000, n])
         assert orc.csr_equal(ref, got), (kind, mask, orc.first_diff(ref, got))
+
+
+@pytest.mark.parametrize("world,n", [(2, 220_000), (5, 200_000)])
+def test_emu_published_segments(emu_lib, orc, world, n):
+    """export through the engine's export buffer (what other processes map once): copies cut down to the reach of the
+    next shard, a straddling block compacted; two rounds on the same engines"""
+    from nlzm_b200 import synth, sharding
+    from nlzm_b200.matchfinder import MatchFinders
+    x = synth.text(n, 3)
+    hb = 16
+    W = 1 << hb
+    ref = orc.find(x, hb, orc.F_ALL)
+    engines = [MatchFinders(emu_lib) for _ in range(world)]
+    ranges = [sharding.shard_range(x.size, r, world) for r in range(world)]
+    try:
+        for step in range(2):
+            for mf, (b, e) in zip(engines, ranges):
+                if step == 0:
+                    mf.Init(hb, x)
+                mf.prepare(b, e)
+            descs = [mf.publish_segments(max(0, e - (W - 1))) for mf, (b, e) in zip(engines, ranges)]
+            assert all(d.pos_begin >= max(0, e - (W - 1)) for ds, (b, e) in zip(descs, ranges) for d in ds)
+            parts = []
+            for r, (mf, (b, e)) in enumerate(zip(engines, ranges)):
+                for q in range(r - 1, -1, -1):
+                    for d in descs[q]:
+                        if d.pos_end > max(0, b - (W - 1)) and d.pos_end <= b:
+                            mf.import_segment(bytes(d))
+                off, st = mf.FindAndUpdate(b, e)
+                parts.append((b, e, off, st))
+            assert orc.csr_equal(ref, sharding.concat_views(parts))
+    finally:
+        for mf in engines:
+            mf.Release()
