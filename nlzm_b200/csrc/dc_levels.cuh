@@ -218,7 +218,39 @@ DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
     const u32 m = (p.n - t0) < NLZM_BASE_TILE ? (p.n - t0) : NLZM_BASE_TILE;
     const u64 abs0 = p.u0 + t0;
     const u64 x_end = p.g.flen + NLZM_X_PAD;                 // bytes [flen, x_end) are zero padding
-    for (u32 i = tid; i < NLZM_BASE_TEXT; i += NLZM_BASE_THREADS) s.text[i] = (abs0 + i < x_end) ? p.x[abs0 + i] : (u8)0;
+    // tile text: 8 bytes per load (the tile may start at any byte offset: two aligned words and a funnel shift)
+    for (u32 i = tid * 8; i < NLZM_BASE_TEXT; i += NLZM_BASE_THREADS * 8) {
+        u64 w = 0;
+        if (abs0 + i + 8 <= x_end) w = load8(p.x, abs0 + i);
+        else for (u32 k = 0; k < 8; k++) if (abs0 + i + k < x_end) w |= (u64)p.x[abs0 + i + k] << (8 * k);
+        if (i + 8 <= NLZM_BASE_TEXT) *(u64 *)(s.text + i) = w;
+        else for (u32 k = 0; i + k < NLZM_BASE_TEXT; k++) s.text[i + k] = (u8)(w >> (8 * k));
+    }
+#if !defined(NLZM_EMU) && defined(__CUDA_ARCH__)
+    {
+        // ranks of a full tile: one bulk copy through the TMA unit (16 KiB, contiguous, 16-byte aligned)
+        __shared__ __align__(8) u64 rank_bar;
+        const u32 bar = nlzm_smem_addr(&rank_bar);
+        const bool bulk = m == NLZM_BASE_TILE && (((uintptr_t)(p.rank + t0)) & 15) == 0;
+        if (bulk) {
+            if (tid == 0) nlzm_mbar_init(bar, 1);
+            __syncthreads();
+            if (tid == 0) {
+                nlzm_mbar_expect_tx(bar, NLZM_BASE_TILE * 4);
+                nlzm_bulk_g2s(nlzm_smem_addr(s.rnk), p.rank + t0, NLZM_BASE_TILE * 4, bar);
+            }
+            nlzm_mbar_wait(bar, 0);
+        }
+        for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
+            if (!bulk) s.rnk[i] = p.rank[t0 + i];
+            if ((t0 + i) >= p.n_valid) s.rnk[i] = NLZM_RANK_PAD;
+            s.arr[0][i] = (u16)i;
+            s.pg[i] = NLZM_L16_NONE;
+            s.ng[i] = NLZM_L16_NONE;
+            s.best[i] = 3;
+        }
+    }
+#else
     for (u32 i = tid; i < m; i += NLZM_BASE_THREADS) {
         s.rnk[i] = (t0 + i) < p.n_valid ? p.rank[t0 + i] : NLZM_RANK_PAD;
         s.arr[0][i] = (u16)i;
@@ -226,6 +258,7 @@ DEV void dc_base_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         s.ng[i] = NLZM_L16_NONE;
         s.best[i] = 3;
     }
+#endif
     NLZM_CTA_SYNC();
     for (u32 i = tid; i < m; i += NLZM_BASE_THREADS)
         s.k4[i] = (u32)s.text[i] | ((u32)s.text[i + 1] << 8) | ((u32)s.text[i + 2] << 16) | ((u32)s.text[i + 3] << 24);
@@ -504,6 +537,27 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
     const u32 nl = l1 - l0, nr = r1 - r0;
     Elem *SL = el + 1;
     Elem *SR = el + nl + 2;
+#if !defined(NLZM_EMU) && defined(__CUDA_ARCH__)
+    {
+        // The tile's two source ranges are contiguous in the level array: the left part with one halo element on each
+        // side, and the right part. One thread hands both to the TMA unit as bulk copies (no LSU traffic, no address
+        // arithmetic in the other 255 threads); completion is counted in bytes on an mbarrier.
+        __shared__ __align__(8) u64 tile_bar;
+        const u32 bar = nlzm_smem_addr(&tile_bar);
+        const u32 g_lo = l0 > 0 ? l0 - 1 : 0;                                    // first left element copied
+        const u32 g_hi = (l0 + nl + 1) < s.l_len ? (l0 + nl + 1) : s.l_len;      // one past the last
+        if (tid == 0) nlzm_mbar_init(bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const u32 bytes_l = (g_hi - g_lo) * (u32)sizeof(Elem), bytes_r = nr * (u32)sizeof(Elem);
+            nlzm_mbar_expect_tx(bar, bytes_l + bytes_r);
+            if (bytes_l) nlzm_bulk_g2s(nlzm_smem_addr(el + (g_lo + 1 - l0)), p.cur + s.base + g_lo, bytes_l, bar);
+            if (bytes_r) nlzm_bulk_g2s(nlzm_smem_addr(SR), p.cur + s.r_beg + r0, bytes_r, bar);
+            *act_n = 0;
+        }
+        nlzm_mbar_wait(bar, 0);
+    }
+#else
     {
         // coalesced 16-byte loads: left part with one halo element on each side, then the right part
         const V16 *GL = (const V16 *)(p.cur + s.base), *GR = (const V16 *)(p.cur + s.r_beg);
@@ -516,6 +570,7 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
         for (u32 c = tid; c < nr * 2; c += NLZM_MT_THREADS) S2[c] = GR[(u64)r0 * 2 + c];
     }
     if (tid == 0) *act_n = 0;
+#endif
     NLZM_CTA_SYNC();
 
     // ---- merge path on keys: NLZM_MT_ITEMS outputs per thread

@@ -76,6 +76,30 @@ static inline int nlzm_smem_opt_in(const void *kernel, size_t smem) {
     }
     return 0;
 }
+// ---- bulk asynchronous copy global -> shared through the TMA unit (cp.async.bulk, SASS UBLKCP), completion counted
+//      in bytes on an mbarrier. One elected thread issues the copies of a tile; everybody waits on the barrier.
+DEV u32 nlzm_smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+DEV void nlzm_mbar_init(u32 bar, u32 arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(arrivals));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+DEV void nlzm_mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+DEV void nlzm_bulk_g2s(u32 dst_smem, const void *src_gmem, u32 bytes, u32 bar) {      // 16-byte aligned, bytes % 16 == 0
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+}
+DEV void nlzm_mbar_wait(u32 bar, u32 parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(bar), "r"(parity) : "memory");
+}
 DEV u32 nlzm_atomic_add(u32 *p, u32 v) { return atomicAdd(p, v); }
 DEV u64 nlzm_atomic_add64(unsigned long long *p, u64 v) { return atomicAdd(p, (unsigned long long)v); }
 DEV u32 nlzm_atomic_max(u32 *p, u32 v) { return atomicMax(p, v); }
