@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libnlzm_mf.so")
+LIB_PATH = os.environ.get("NLZM_MF_LIB") or os.path.join(HERE, "csrc", "libnlzm_mf.so")   # override: A/B builds (tools/)
 
 HT2, HT3, BT4, RK256, ALL = 1, 2, 4, 8, 15
 

@@ -419,6 +419,9 @@ NLZM_KERNEL_CTA_OCC(dc_base, DcParams, NLZM_BASE_THREADS, NLZM_BASE_MINBLOCKS)
 #ifndef NLZM_MT_THREADS
 #define NLZM_MT_THREADS 256
 #endif
+#ifndef NLZM_MT_TMA
+#define NLZM_MT_TMA 1                    // 1: tiles staged by TMA bulk copies, 0: by 16-byte loads of all threads
+#endif
 #ifndef NLZM_MT_ITEMS
 #define NLZM_MT_ITEMS 4
 #endif
@@ -537,7 +540,7 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
     const u32 nl = l1 - l0, nr = r1 - r0;
     Elem *SL = el + 1;
     Elem *SR = el + nl + 2;
-#if !defined(NLZM_EMU) && defined(__CUDA_ARCH__)
+#if !defined(NLZM_EMU) && defined(__CUDA_ARCH__) && NLZM_MT_TMA
     {
         // The tile's two source ranges are contiguous in the level array: the left part with one halo element on each
         // side, and the right part. One thread hands both to the TMA unit as bulk copies (no LSU traffic, no address
@@ -555,7 +558,7 @@ DEV void dc_merge_tile_cta(const DcParams &p, u32 bid, u32 tid, u8 *smem) {
             if (bytes_r) nlzm_bulk_g2s(nlzm_smem_addr(SR), p.cur + s.r_beg + r0, bytes_r, bar);
             *act_n = 0;
         }
-        nlzm_mbar_wait(bar, 0);
+        if (tid < 32) nlzm_mbar_wait(bar, 0);          // one warp polls; the others sleep in the barrier below
     }
 #else
     {
