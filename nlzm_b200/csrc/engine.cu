@@ -171,6 +171,7 @@ struct nlzm_mf {
     PrimTemp tmp;
     DevBuf tmpbuf;
     u32 tuple_cap_mult = 6;
+    u64 tuple_cap_extra = 1u << 20;        // options "tuple_cap_mult" / "tuple_cap_extra": candidate tuple capacity = range * mult + extra
     u64 ht_margin = NLZM_HT_MARGIN;        // options (nlzm_mf_set_option): tuning / test knobs
     u32 ht_coarse_log = NLZM_HT_COARSE_LOG;
     bool rk_all_hits = false, rk_overflowed = false;
@@ -876,7 +877,7 @@ int nlzm_mf::compute(u64 b, u64 e, Slot &s) {
     const bool was_prepared = prepared && prep_b == b && prep_e == e;
     if (was_prepared) prepared = false;
     for (int attempt = 0; attempt < 4; attempt++) {
-        const u64 cap = n_own * tuple_cap_mult + (1u << 20);
+        const u64 cap = n_own * tuple_cap_mult + tuple_cap_extra;
         if (cap >= 0xFFFFFFF0ull) return fail(NLZM_MF_E_OVERFLOW, "candidate tuple capacity exceeds 2^32");
         const bool continue_prepared = was_prepared && attempt == 0;
         CKI(ensure(tk[0], cap * 8)); CKI(ensure(tk[1], cap * 8));
@@ -967,7 +968,7 @@ int nlzm_mf::prepare_impl(u64 b, u64 e) {
     }
     const u64 n_own = e - b;
     for (int attempt = 0; attempt < 4; attempt++) {
-        const u64 cap = n_own * tuple_cap_mult + (1u << 20);
+        const u64 cap = n_own * tuple_cap_mult + tuple_cap_extra;
         if (cap >= 0xFFFFFFF0ull) return fail(NLZM_MF_E_OVERFLOW, "candidate tuple capacity exceeds 2^32");
         CKI(ensure(tk[0], cap * 8)); CKI(ensure(tk[1], cap * 8));
         CKI(ensure(tv[0], cap * 4)); CKI(ensure(tv[1], cap * 4));
@@ -1456,6 +1457,8 @@ int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value) {
     Turn turn(mf);
     const std::string k(key);
     if (k == "ht_margin") { mf->ht_margin = value; return 0; }
+    if (k == "tuple_cap_mult") { mf->tuple_cap_mult = value ? (u32)value : 1u; return 0; }
+    if (k == "tuple_cap_extra") { mf->tuple_cap_extra = value; return 0; }
     if (k == "retain") { mf->retain = value != 0; if (!mf->retain) mf->segs.clear(); return 0; }
     if (k == "max_segments") { mf->max_segments = (u32)value; return 0; }
     if (k == "ht_coarse_log") {

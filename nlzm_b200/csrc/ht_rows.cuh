@@ -41,7 +41,9 @@ struct HtCfg {
 #define NLZM_HT_MARGIN 0ull                    // PS/PL/PR start this far before the answered range (rounded down to a coarse
                                                // tile): chains that reach further back end in the snapshot of the cells
                                                // at that point, so the per-position walk does not grow with the prefix
+#ifndef NLZM_HT_THREADS
 #define NLZM_HT_THREADS 256
+#endif
 #define NLZM_HT_STAGE 2048u                     // text bytes staged in shared memory by k_ht_prev
 
 HD u32 ht_hash(const u8 *__restrict__ x, u64 a, u32 nbytes) {

@@ -302,3 +302,25 @@ def test_emu_published_segments(emu_lib, orc, world, n):
     finally:
         for mf in engines:
             mf.Release()
+
+
+def test_emu_tuple_overflow_is_retried(emu_lib, orc):
+    """a candidate buffer that is too small: the engine grows it and redoes the range (also a prepared one, and one
+    that queries retained segments) — same result"""
+    from nlzm_b200 import synth
+    from nlzm_b200.matchfinder import MatchFinders
+    x = synth.text(90_000, 77)
+    ref = orc.find(x, 15, orc.F_ALL)
+    with MatchFinders(emu_lib) as mf:
+        mf.Init(15, x)
+        mf.set_option("tuple_cap_extra", 0)
+        mf.set_option("tuple_cap_mult", 1)
+        got, used = _blocks(mf, [0, 40_000, 90_000])
+        assert orc.csr_equal(ref, got) and used[1] > 0
+    with MatchFinders(emu_lib) as mf:
+        mf.Init(15, x)
+        mf.set_option("tuple_cap_extra", 0)
+        mf.set_option("tuple_cap_mult", 1)
+        mf.prepare(0, 40_000)
+        got, _ = _blocks(mf, [0, 40_000])
+        assert orc.csr_equal((ref[0][:40_001], ref[1][:int(ref[0][40_000])], ref[2][:int(ref[0][40_000])]), got)

@@ -174,3 +174,37 @@ def test_properties_256mb_window(cuda_lib):
             _check_properties(x, off, st, b, 1 << 28)
             total += st.size
     assert total > x.size          # redundant data: several steps per position
+
+
+@pytest.mark.parametrize("kind", ["zeros_ones", "period", "ab", "words", "text"])
+def test_retained_segments_adversarial_and_overflow(cuda_lib, orc, kind):
+    """consecutive blocks (retained segments, text-order cross merge), small HT coarse tiles (cell snapshot + warp
+    scans of the far prefix) and a forced candidate-buffer overflow, on inputs whose suffixes tie for hundreds of
+    bytes and end in a zero run"""
+    from nlzm_b200 import synth
+    from test_fuzz import _gen
+    from nlzm_b200.matchfinder import MatchFinders
+    n = 700_000
+    x = synth.text(n, 5) if kind == "text" else _gen(kind, n, np.random.default_rng(11))
+    if kind == "zeros_ones":
+        x[-3000:] = 0
+    hb = 17
+    ref = orc.find(x, hb, orc.F_ALL)
+    cuts = [0, 150_000, 290_001, 431_000, 650_000, n]
+    with MatchFinders(cuda_lib) as mf:
+        mf.Init(hb, x)
+        mf.set_option("ht_coarse_log", 13)
+        if kind in ("text", "words"):
+            mf.set_option("tuple_cap_extra", 0)
+            mf.set_option("tuple_cap_mult", 1)
+        offs, ds, ls, base, used = [np.zeros(1, np.uint64)], [], [], 0, []
+        for i, (b, e) in enumerate(zip(cuts[:-1], cuts[1:])):
+            off, st = mf.FindAndUpdate(b, e, slot=i & 1)
+            used.append(int(mf.stats().segments_queried))
+            offs.append(off[1:].astype(np.uint64) + base)
+            base += int(off[-1])
+            ds.append(st["dist"].copy())
+            ls.append(st["len"].copy())
+    got = (np.concatenate(offs), np.concatenate(ds), np.concatenate(ls))
+    assert orc.csr_equal(ref, got), (kind, orc.first_diff(ref, got))
+    assert all(u > 0 for u in used[1:]), used
