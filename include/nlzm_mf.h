@@ -158,7 +158,10 @@ typedef struct {
 int nlzm_mf_prepare(nlzm_mf *mf, uint64_t begin, uint64_t end);
 int nlzm_mf_export_segments(nlzm_mf *mf, nlzm_mf_segment *out, uint32_t cap, uint32_t *n_out);
 /* via: 0 = elems_alloc / ptrs_alloc are device pointers of this process (peer copy), 1 = open the IPC handles,
- *      2 = elems_alloc / ptrs_alloc are HOST copies of the two slices made with nlzm_mf_read_segment */
+ *      2 = elems_alloc / ptrs_alloc are HOST copies of the two slices made with nlzm_mf_read_segment;
+ *      | 0x100 (with 0 or 1): asynchronous — the copies are queued on the engine's copy stream and the call
+ *      returns; the next find runs its HT and RK stages while they arrive and waits for them before it
+ *      queries the segments. The exporter must keep the source unchanged until that find has returned. */
 /* Export for OTHER PROCESSES: copies this engine's own segments, cut down to positions >= from_pos, into one export
  * buffer that lives as long as the engine and describes the copies (call with out == NULL to get the count). The
  * descriptors carry the CUDA IPC handle of that buffer: an importer maps it once, however often it is refilled. */

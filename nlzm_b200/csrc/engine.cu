@@ -178,6 +178,8 @@ struct nlzm_mf {
     bool retain = true;                    // option "retain": keep the sorted blocks of a find for the next one
     u32 max_segments = 8;                  // option "max_segments": more retained segments than this behind a range => halo mode
 
+    cudaEvent_t import_ev = nullptr;       // last asynchronous segment import on st_copy (nlzm_mf_import_segment, via | 0x100)
+    bool imports_pending = false;
     std::vector<Segment> segs;             // retained, ascending by position
     std::vector<Segment> fresh;            // sorted blocks of the find in progress (own universe)
     u64 fresh_u0 = 0;
@@ -903,24 +905,35 @@ int nlzm_mf::compute(u64 b, u64 e, Slot &s) {
         Ev e0, e1, e2, e3, e4;
         cudaEventRecord(e0, st);
         int r = 0;
+        std::vector<Segment> behind_all;
+        bool have_behind = false;
         if (n_own > 0) {
             if ((mask & NLZM_MF_BT4) && g.flen >= 4) {
                 // window behind the range: from retained segments when they cover it, else re-ranked with the range.
                 // A prepared range has no halo by construction: its segments must have been imported by now.
-                std::vector<Segment> behind;
+                std::vector<Segment> &behind = behind_all;
                 const bool covered = covered_by_segments(b, behind);
                 if (was_prepared && !covered)
                     return fail(NLZM_MF_E_STATE, "prepared range: the window behind it is not covered by imported segments");
                 const u64 halo_b = b > (u64)(g.W - 1) ? b - (g.W - 1) : 0;
                 if (!continue_prepared) r = stage_bt4_own(b, e, covered ? b : halo_b);
-                if (r == 0 && covered) r = stage_bt4_cross(b, e, behind);
+                if (!covered) behind.clear();
+                have_behind = true;
             }
+            // stages H and R do not depend on the segments behind the range: they run while asynchronous imports
+            // are still crossing NVLink; the cross passes wait for the copies
             cudaEventRecord(e1, st);
             if (r == 0 && (mask & NLZM_MF_HT2)) { HtCfg c{1, 12, 2}; r = stage_ht(b, e, c); }
             if (r == 0 && (mask & NLZM_MF_HT3)) { HtCfg c{2, g.ht3_bits, 3}; r = stage_ht(b, e, c); }
             cudaEventRecord(e2, st);
             if (r == 0 && (mask & NLZM_MF_RK256)) r = stage_rk(b, e);
             cudaEventRecord(e3, st);
+            if (r == 0 && have_behind && !behind_all.empty()) {
+#ifndef NLZM_EMU
+                if (imports_pending) { CK(cudaStreamWaitEvent(st, import_ev, 0)); imports_pending = false; }
+#endif
+                r = stage_bt4_cross(b, e, behind_all);
+            }
         } else {
             cudaEventRecord(e1, st); cudaEventRecord(e2, st); cudaEventRecord(e3, st);
         }
@@ -943,6 +956,9 @@ int nlzm_mf::compute(u64 b, u64 e, Slot &s) {
         if (r) { fresh.clear(); return r; }
         break;
     }
+#ifndef NLZM_EMU
+    if (imports_pending) { cudaStreamSynchronize(st_copy); imports_pending = false; }   // imported but not queried: let the copies land before the buffers go
+#endif
     retain_fresh(e);
     return 0;
 }
@@ -959,6 +975,9 @@ int nlzm_mf::prepare_impl(u64 b, u64 e) {
     CK(cudaSetDevice(device));
 #endif
     prepared = false;
+#ifndef NLZM_EMU
+    if (imports_pending) { cudaStreamSynchronize(st_copy); imports_pending = false; }   // imports nobody waited for
+#endif
     stats.ms_import = 0;
     stats.bytes_imported = 0;
     {
@@ -1130,6 +1149,9 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
     cudaSetDevice(mf->device);
 #endif
     for (auto &s : mf->slot) if (s.worker.joinable()) s.worker.join();
+#ifndef NLZM_EMU
+    if (mf->st_copy) cudaStreamSynchronize(mf->st_copy);
+#endif
     mf->fresh.clear();
     mf->prep_fresh.clear();
     mf->segs.clear();                                  // buffers go back to the pool, which is freed below
@@ -1152,6 +1174,7 @@ void nlzm_mf_destroy(nlzm_mf *mf) {
                      &mf->hit_v[1], &mf->hit_len, &mf->iv, &mf->val_k, &mf->val_v, &mf->scalars, &mf->tmpbuf, &mf->prep_tk, &mf->prep_tv, &mf->xstage};
     for (DevBuf *b : all) mf->release(*b);
 #ifndef NLZM_EMU
+    if (mf->import_ev) cudaEventDestroy(mf->import_ev);
     if (mf->st) cudaStreamDestroy(mf->st);
     if (mf->st_copy) cudaStreamDestroy(mf->st_copy);
     if (mf->h_words) cudaFreeHost(mf->h_words);
@@ -1173,6 +1196,9 @@ static int set_input_common(nlzm_mf *mf, const void *src, uint64_t len, bool fro
         e = cudaMemcpyAsync(mf->x.p, src, len, from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, mf->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
     if (e != cudaSuccess) return mf->fail((int)e, std::string("set_input: ") + cudaGetErrorString(e));
+#ifndef NLZM_EMU
+    if (mf->imports_pending) { cudaStreamSynchronize(mf->st_copy); mf->imports_pending = false; }
+#endif
     mf->segs.clear();                                  // segments describe the previous bytes
     mf->fresh.clear();
     mf->prep_fresh.clear();
@@ -1306,6 +1332,9 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
     int r = mf->ensure_pooled(bufs->el, (size_t)d->elems_bytes);
     if (r == 0) r = mf->ensure_pooled(bufs->ptr, (size_t)d->ptrs_bytes);
     if (r) return r;
+    const bool async = (via_ipc & 0x100) != 0;           // copies go to the copy stream; the next find waits for them
+    via_ipc &= 0xFF;
+    cudaStream_t cst = async ? mf->st_copy : mf->st;
     const u8 *src_el = (const u8 *)d->elems_alloc, *src_ptr = (const u8 *)d->ptrs_alloc;
     if (via_ipc == 2) {
         // elems_alloc / ptrs_alloc are HOST copies of the two slices (nlzm_mf_read_segment on the exporting side)
@@ -1336,24 +1365,34 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
         src_ptr = (const u8 *)open_ptr;
     }
     Ev c0, c1;
-    cudaEventRecord(c0, mf->st);
+    cudaEventRecord(c0, cst);
     cudaError_t e;
     if (via_ipc) {
         // an IPC mapping is an ordinary device pointer of this process (unified addressing finds the owner GPU)
-        e = cudaMemcpyAsync(bufs->el.p, src_el + d->elems_offset_bytes, (size_t)d->elems_bytes, cudaMemcpyDefault, mf->st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(bufs->ptr.p, src_ptr + d->ptrs_offset_bytes, (size_t)d->ptrs_bytes, cudaMemcpyDefault, mf->st);
+        e = cudaMemcpyAsync(bufs->el.p, src_el + d->elems_offset_bytes, (size_t)d->elems_bytes, cudaMemcpyDefault, cst);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(bufs->ptr.p, src_ptr + d->ptrs_offset_bytes, (size_t)d->ptrs_bytes, cudaMemcpyDefault, cst);
     } else {
-        e = cudaMemcpyPeerAsync(bufs->el.p, mf->device, src_el + d->elems_offset_bytes, d->device, (size_t)d->elems_bytes, mf->st);
-        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(bufs->ptr.p, mf->device, src_ptr + d->ptrs_offset_bytes, d->device, (size_t)d->ptrs_bytes, mf->st);
+        e = cudaMemcpyPeerAsync(bufs->el.p, mf->device, src_el + d->elems_offset_bytes, d->device, (size_t)d->elems_bytes, cst);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(bufs->ptr.p, mf->device, src_ptr + d->ptrs_offset_bytes, d->device, (size_t)d->ptrs_bytes, cst);
     }
-    cudaEventRecord(c1, mf->st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(mf->st);
-    if (e == cudaSuccess) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c0, c1);
-        std::lock_guard<std::mutex> l(mf->stats_mu);
-        mf->stats.ms_import += ms;
-        mf->stats.bytes_imported += d->elems_bytes + d->ptrs_bytes;
+    cudaEventRecord(c1, cst);
+    if (async) {
+        if (e == cudaSuccess) {
+            if (!mf->import_ev) cudaEventCreateWithFlags(&mf->import_ev, cudaEventDisableTiming);
+            cudaEventRecord(mf->import_ev, cst);
+            mf->imports_pending = true;
+            std::lock_guard<std::mutex> l(mf->stats_mu);
+            mf->stats.bytes_imported += d->elems_bytes + d->ptrs_bytes;
+        }
+    } else {
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cst);
+        if (e == cudaSuccess) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c0, c1);
+            std::lock_guard<std::mutex> l(mf->stats_mu);
+            mf->stats.ms_import += ms;
+            mf->stats.bytes_imported += d->elems_bytes + d->ptrs_bytes;
+        }
     }
     if (e != cudaSuccess) return mf->fail((int)e, std::string("segment copy: ") + cudaGetErrorString(e));
 #else
@@ -1419,6 +1458,9 @@ int nlzm_mf_publish_segments(nlzm_mf *mf, uint64_t from_pos, nlzm_mf_segment *ou
 int nlzm_mf_drop_segments(nlzm_mf *mf) {
     if (!mf) return NLZM_MF_E_ARG;
     Turn turn(mf);
+#ifndef NLZM_EMU
+    if (mf->imports_pending) { cudaStreamSynchronize(mf->st_copy); mf->imports_pending = false; }
+#endif
     mf->segs.clear();
     mf->fresh.clear();
     mf->prep_fresh.clear();

@@ -176,12 +176,16 @@ class ShardedFind:
                         if self.transport == "host":
                             mf.import_segment(item["desc"], host_copy=item["host"])
                         else:
-                            mf.import_segment(item["desc"], via=1 if self.transport == "ipc" else 0)
+                            # asynchronous: the copies overlap this rank's HT / RK stages (find waits for them)
+                            mf.import_segment(item["desc"], via=(1 if self.transport == "ipc" else 0) | 0x100)
                         self.imported_bytes += (pe - pb) * 48
         except Exception as ex:  # noqa: BLE001
             err = f"rank {self.rank}: {ex}"
         t = self._tick("import", t)
-        (self._agree_fast if self._fast else self._agree)(err)     # nobody may recycle a buffer a neighbour is still reading
+        # every rank learns whether an import failed anywhere. (Asynchronous copies may still be in flight here: the
+        # export buffers are only rewritten by the next publish, which comes after the agreement at the END of this
+        # run, and every rank's find — which waits for its imports — has returned by then.)
+        (self._agree_fast if self._fast else self._agree)(err)
         t = self._tick("agree_wait", t)
         try:
             res = find(first[0], first[1], 0)

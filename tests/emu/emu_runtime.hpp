@@ -26,3 +26,5 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEve
     return 0;
 }
 static inline cudaError_t cudaGetLastError() { return 0; }
+#define cudaEventDisableTiming 0
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, int) { return cudaEventCreate(e); }
