@@ -179,6 +179,8 @@ int nlzm_mf_trim_segments(nlzm_mf *mf, uint64_t from_pos);
  *   "ht_coarse_log"  log2 of the coarse table spacing of the far prefix (default 20)
  *   "tuple_cap_mult", "tuple_cap_extra"   candidate tuple capacity of a find = positions * mult + extra (defaults 6, 2^20);
  *                    on overflow the engine doubles mult and redoes the range (tests force that path)
+ *   "rk_restart"     positions before a range from which stage R looks hits up when it tries to restart its
+ *                    carried-match machine behind a hit-free stretch instead of at the last ring shift (default 2^18)
  *   "retain"         0 = forget the segments after every find (default 1)
  *   "max_segments"   a range with more retained segments than this behind it is computed from scratch (default 8) */
 int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value);

@@ -96,7 +96,7 @@ __global__ void k_words_to_host(const u32 *src, volatile u32 *dst, u32 n) { for 
 #endif
 
 // device scalars live in one small buffer (u32 slots)
-enum { SC_SUM = 0 /* u64 */, SC_RK_HITS = 8, SC_RK_INTERVALS = 9, SC_RK_VALID = 10 };
+enum { SC_SUM = 0 /* u64 */, SC_RK_HITS = 8, SC_RK_INTERVALS = 9, SC_RK_VALID = 10, SC_RK_OK = 11 };
 
 #define CK(expr)                                                                                   \
     do {                                                                                           \
@@ -175,6 +175,7 @@ struct nlzm_mf {
     u64 ht_margin = NLZM_HT_MARGIN;        // options (nlzm_mf_set_option): tuning / test knobs
     u32 ht_coarse_log = NLZM_HT_COARSE_LOG;
     bool rk_all_hits = false, rk_overflowed = false;
+    u64 rk_restart = 1u << 18;             // option "rk_restart": how far before a range stage R starts looking for hits
     bool retain = true;                    // option "retain": keep the sorted blocks of a find for the next one
     u32 max_segments = 8;                  // option "max_segments": more retained segments than this behind a range => halo mode
 
@@ -760,13 +761,19 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     if (g.flen < NLZM_RK_BLOCK) return 0;
     const u64 rk_e = own_e < g.flen - 255 ? own_e : g.flen - 255;    // RK is called while 256 bytes are visible
     if (rk_e <= own_b) return 0;
-    // the carry state machine restarts cleanly at a ring shift: begin at the last one at or before own_b
-    u64 rk_b = 0;
+    // the carry state machine restarts cleanly at a ring shift: the last one at or before own_b ...
+    u64 rk_b_shift = 0;
     const u32 ep = geom_epoch(g, own_b);
     if (ep > 0) {
         u64 k = (((u64)(ep + 1) << g.hb) + g.cs - 1) / g.cs;
-        rk_b = k * g.cs;
+        rk_b_shift = k * g.cs;
     }
+    // ... and behind any 65536 positions without a valid hit (no carry outlives them). First try: look hits up only from
+    // a little before the range and let the chain kernel find such a stretch; if there is none (dense hits), redo from
+    // the ring shift. A late range then costs what its own positions cost, not what the prefix since the shift costs.
+    const bool try_short = own_b > rk_b_shift + rk_restart + 2 * NLZM_RK_CARRY_MAX;
+  for (int rk_attempt = try_short ? 0 : 1; rk_attempt < 2; rk_attempt++) {
+    const u64 rk_b = rk_attempt == 0 ? own_b - rk_restart : rk_b_shift;
     const u64 n_blk = (rk_e + NLZM_RK_BLOCK - 1) / NLZM_RK_BLOCK;    // blocks starting before rk_e (each has 256 bytes)
     const u64 n_slots = 1ull << g.rk_bits;
     CKI(ensure(hblk, n_blk * 4));
@@ -804,7 +811,7 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
         rk_overflowed = true;
         return fail(NLZM_MF_E_OVERFLOW, "RK raw-hit buffer overflow");
     }
-    if (n_hits == 0) return 0;
+    if (n_hits == 0) return 0;                   // no raw hit in the looked-up prefix either: nothing is carried into the range
     // extension of every raw hit (any order); the few that are real hits are compacted, sorted by
     // position and fed to the sequential carry state machine
     u32 *n_valid = scalars.as<u32>() + SC_RK_VALID;
@@ -823,12 +830,16 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     int hsel = 0;
     CKI(prim_sort_pairs64(tmp, hit_k[1].as<u64>(), val_k.as<u64>(), hit_v[1].as<u32>(), val_v.as<u32>(), nv, 0, (int)bits_for(g.flen + 1), st, &hsel));
     RkChainParams cp{g, hsel ? val_k.as<u64>() : hit_k[1].as<u64>(), hsel ? val_v.as<u32>() : hit_v[1].as<u32>(),
-                     hit_v[0].as<u32>(), hit_len.as<u32>(), n_valid, iv.as<RkInterval>(), n_iv};
+                     hit_v[0].as<u32>(), hit_len.as<u32>(), n_valid, iv.as<RkInterval>(), n_iv,
+                     rk_b, own_b, rk_attempt == 0 ? 1u : 0u, scalars.as<u32>() + SC_RK_OK};
     launch_rk_chain(cp, 1, st);
-    u32 niv = 0;
-    CKI(fetch_words(n_iv, &niv, 1));
+    u32 res[3] = {0, 0, 0};                      // n_iv, n_valid, ok (consecutive scalars)
+    CKI(fetch_words(n_iv, res, 3));
+    if (rk_attempt == 0 && !res[2]) continue;    // hits too dense for a restart point: from the ring shift
     RkExpandParams ex{g, iv.as<RkInterval>(), own_b, own_e, (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
-    launch_rk_expand(ex, niv, st);
+    launch_rk_expand(ex, res[0], st);
+    return 0;
+  }
     return 0;
 }
 
@@ -1499,6 +1510,7 @@ int nlzm_mf_set_option(nlzm_mf *mf, const char *key, uint64_t value) {
     Turn turn(mf);
     const std::string k(key);
     if (k == "ht_margin") { mf->ht_margin = value; return 0; }
+    if (k == "rk_restart") { mf->rk_restart = value; return 0; }
     if (k == "tuple_cap_mult") { mf->tuple_cap_mult = value ? (u32)value : 1u; return 0; }
     if (k == "tuple_cap_extra") { mf->tuple_cap_extra = value; return 0; }
     if (k == "retain") { mf->retain = value != 0; if (!mf->retain) mf->segs.clear(); return 0; }

@@ -156,7 +156,15 @@ struct RkChainParams {
     const u32 *hit_dist; const u32 *hit_len;             // indexed by raw hit index
     const u32 *n_valid;
     RkInterval *iv; u32 *n_iv;
+    // Where the machine may start. A carry lives at most 65535 positions (uint16 length, NLZM.cpp:759-760), so after
+    // 65536 positions without a valid hit nothing is carried: the state is "no carry" whatever came before. When the
+    // hits were only looked up from `known_from` on (not from the last ring shift), the walk starts behind the latest
+    // such stretch that ends at or before `own_b`; if there is none, *ok = 0 and the caller redoes the range in full.
+    u64 known_from, own_b;
+    u32 need_restart;
+    u32 *ok;
 };
+#define NLZM_RK_CARRY_MAX 65536ull
 
 HD u64 rk_carry_end(const Geom &g, u64 ca, u32 cl) {
     // a carry dies when its length is used up or at the next ring shift (P - carry_to wraps, NLZM.cpp:1057)
@@ -178,6 +186,18 @@ DEV void rk_chain_body(const RkChainParams &p, u64) {
     u32 cl = 0, cd = 0, cep = 0, niv = 0;
     u64 ca = 0;
     u32 i = 0;
+    *p.ok = 1;
+    if (p.need_restart) {
+        u64 last = p.known_from;                         // nothing is known about hits before this position
+        u32 start = 0xFFFFFFFFu, j = 0;
+        for (; j < n && p.valid_pos[j] < p.own_b; j++) {
+            if (p.valid_pos[j] - last >= NLZM_RK_CARRY_MAX) start = j;
+            last = p.valid_pos[j];
+        }
+        if (p.own_b - last >= NLZM_RK_CARRY_MAX) start = j;
+        if (start == 0xFFFFFFFFu) { *p.ok = 0; *p.n_iv = 0; return; }
+        i = start;
+    }
     while (i < n) {
         const u64 a = p.valid_pos[i];
         const u32 ri = p.valid_idx[i];

@@ -324,3 +324,22 @@ def test_emu_tuple_overflow_is_retried(emu_lib, orc):
         mf.prepare(0, 40_000)
         got, _ = _blocks(mf, [0, 40_000])
         assert orc.csr_equal((ref[0][:40_001], ref[1][:int(ref[0][40_000])], ref[2][:int(ref[0][40_000])]), got)
+
+
+@pytest.mark.parametrize("kind", ["zeros", "longrange", "period"])
+def test_emu_rk_restart_point(emu_lib, orc, kind):
+    """stage R of a late range: hits are looked up from a little before the range only and the carried-match machine
+    starts behind a stretch of 65536 hit-free positions (sparse hits), or the range is redone from the last ring shift
+    (dense hits); both must equal the sequential reference"""
+    from nlzm_b200 import synth
+    from nlzm_b200.matchfinder import MatchFinders
+    from test_fuzz import _gen
+    n = 700_000
+    x = _gen(kind, n, np.random.default_rng(3)) if kind == "period" else synth.make(kind, n)
+    ref = orc.find(x, 24, orc.F_RK256)
+    with MatchFinders(emu_lib) as mf:
+        mf.Init(24, x, finder_mask=orc.F_RK256)
+        mf.set_option("rk_restart", 70_000)
+        got, _ = _blocks(mf, [0, 260_000, 480_001, n])
+    assert orc.csr_equal(ref, got), (kind, orc.first_diff(ref, got))
+    assert ref[1].size > 0
