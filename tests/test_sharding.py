@@ -14,27 +14,46 @@ import torch.multiprocessing as mp
 from conftest import ROOT
 
 
-def _worker(rank, world, port, q):
+def _input(cuda):
+    from nlzm_b200 import synth
+    if cuda:
+        return np.concatenate([synth.longrange(1_600_000, 91), synth.text(1_400_000, 92)]), 20, 1_100_000
+    return synth.longrange(110_000, 91), 15, 40_000
+
+
+def _worker(rank, world, port, q, cuda=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import ctypes as C
-    from nlzm_b200 import _lib, synth, sharding
+    from nlzm_b200 import _lib, sharding
     from nlzm_b200.matchfinder import MatchFinders
-    emu = _lib.bind_prototypes(C.CDLL(os.path.join(ROOT, "tests", "emu", "libnlzm_mf_emu.so")))
-    x = synth.longrange(110_000, 91)                     # replicated input
+    if cuda:
+        # the product library; both processes drive the SAME GPU, so the CUDA IPC path (publish_segments, one mapping
+        # per importer, asynchronous import) is exercised and checked on a one-GPU box as well
+        emu = _lib.load()
+    else:
+        emu = _lib.bind_prototypes(C.CDLL(os.path.join(ROOT, "tests", "emu", "libnlzm_mf_emu.so")))
+    x, hb, block = _input(cuda)                          # replicated input
     b, e = sharding.shard_range(x.size, rank, world)
     mine = []
     with MatchFinders(emu) as mf:
-        mf.Init(15, x)
-        # the segment hand-over protocol of the bench, staged through the host (two CPU processes share no memory)
-        sf = sharding.ShardedFind(mf, rank, world, 1 << 15, group=None, transport="host")
-        blocks = sharding.split_blocks(b, e, 40_000)
+        mf.Init(hb, x)
+        # the segment hand-over protocol of the bench: CUDA IPC on the GPU, staged through the host on the CPU (two
+        # CPU processes share no memory)
+        sf = sharding.ShardedFind(mf, rank, world, 1 << hb, group=None, transport="ipc" if cuda else "host")
+        blocks = sharding.split_blocks(b, e, block)
 
         def find(bb, ee, i):
             off, st = mf.FindAndUpdate(bb, ee, slot=i & 1)
             mine.append((bb, ee, off, st, int(mf.stats().segments_queried)))
-        sf.run(blocks, find)
+        try:
+            sf.run(blocks, find)
+        except RuntimeError as ex:                       # raised on every rank at the same protocol point
+            if rank == 0:
+                q.put(("error", str(ex)))
+            dist.destroy_process_group()
+            return
         # the fixed-size descriptor exchange of the GPU transports carries the same information as the object path
         descs = [{"desc": bytes(d), "pos": (int(d.pos_begin), int(d.pos_end))} for d in mf.export_segments()]
         fast = sharding.ShardedFind(mf, rank, world, 1 << 15, group=None, transport="ipc")._exchange_descs(None, descs)
@@ -52,23 +71,52 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharding(emu_lib, orc):
-    from nlzm_b200 import synth, sharding
+def _run_two_ranks(orc, cuda):
+    from nlzm_b200 import sharding
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + os.getpid() % 2000 + (17 if cuda else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, cuda)) for r in range(2)]
     for p in procs:
         p.start()
-    parts, tmax = q.get()
+    import time
+    deadline = time.time() + (600 if cuda else 180)
+    got = None
+    while got is None and time.time() < deadline:       # the result must be taken before the writer can exit
+        if not q.empty():
+            got = q.get()
+        elif any(p.exitcode not in (None, 0) for p in procs):
+            break
+        else:
+            time.sleep(0.2)
     for p in procs:
-        p.join(60)
-        assert p.exitcode == 0
+        p.join(30)
+    codes = [p.exitcode for p in procs]
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+    assert got is not None and codes == [0, 0], codes
+    if got[0] == "error":
+        if cuda and "Ipc" in got[1]:
+            pytest.skip("CUDA IPC between two processes is not available here: " + got[1][:200])
+        pytest.fail(got[1])
+    parts, tmax = got
     assert tmax == 2.0
-    x = synth.longrange(110_000, 91)
+    x, hb, _ = _input(cuda)
     off, dist_, ln = sharding.concat_views([p for rank_parts in parts for p in rank_parts])
-    ref = orc.find(x, 15, orc.F_ALL)
-    assert orc.csr_equal(ref, (off, dist_, ln))
+    ref = orc.find(x, hb, orc.F_ALL)
+    assert orc.csr_equal(ref, (off, dist_, ln)), orc.first_diff(ref, (off, dist_, ln))
+
+
+def test_two_rank_sharding(emu_lib, orc):
+    _run_two_ranks(orc, cuda=False)
+
+
+@pytest.mark.gpu
+def test_two_processes_share_segments_over_cuda_ipc(cuda_lib, orc):
+    """two processes (one engine each, both on cuda:0): the window behind the second shard arrives through the first
+    engine's export buffer and a CUDA IPC mapping, asynchronously; the gathered candidates equal the oracle"""
+    _run_two_ranks(orc, cuda=True)
 
 
 def test_shard_ranges_cover():
