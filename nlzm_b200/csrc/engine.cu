@@ -313,6 +313,7 @@ struct nlzm_mf {
                                            // that holds the published copies of this engine's segments
     int stage_ht(u64 own_b, u64 own_e, const HtCfg &c);
     int stage_rk(u64 own_b, u64 own_e);
+    int stage_rk_from(u64 own_b, u64 own_e, u64 rk_e, u64 rk_b, bool need_restart, bool &done);
     int stage_merge(u64 own_b, u64 own_e, Slot &s);
     int compute(u64 b, u64 e, Slot &s);
     int find_impl(u64 b, u64 e, int slot, bool to_host, u64 ticket);
@@ -772,8 +773,18 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     // a little before the range and let the chain kernel find such a stretch; if there is none (dense hits), redo from
     // the ring shift. A late range then costs what its own positions cost, not what the prefix since the shift costs.
     const bool try_short = own_b > rk_b_shift + rk_restart + 2 * NLZM_RK_CARRY_MAX;
-  for (int rk_attempt = try_short ? 0 : 1; rk_attempt < 2; rk_attempt++) {
-    const u64 rk_b = rk_attempt == 0 ? own_b - rk_restart : rk_b_shift;
+    if (try_short) {
+        bool done = false;
+        CKI(stage_rk_from(own_b, own_e, rk_e, own_b - rk_restart, true, done));
+        if (done) return 0;
+    }
+    bool done = false;
+    return stage_rk_from(own_b, own_e, rk_e, rk_b_shift, false, done);
+}
+
+// hits looked up from rk_b on; need_restart: the state at rk_b is unknown, *done = false if no restart point exists
+int nlzm_mf::stage_rk_from(u64 own_b, u64 own_e, u64 rk_e, u64 rk_b, bool need_restart, bool &done) {
+    done = true;
     const u64 n_blk = (rk_e + NLZM_RK_BLOCK - 1) / NLZM_RK_BLOCK;    // blocks starting before rk_e (each has 256 bytes)
     const u64 n_slots = 1ull << g.rk_bits;
     CKI(ensure(hblk, n_blk * 4));
@@ -831,15 +842,13 @@ int nlzm_mf::stage_rk(u64 own_b, u64 own_e) {
     CKI(prim_sort_pairs64(tmp, hit_k[1].as<u64>(), val_k.as<u64>(), hit_v[1].as<u32>(), val_v.as<u32>(), nv, 0, (int)bits_for(g.flen + 1), st, &hsel));
     RkChainParams cp{g, hsel ? val_k.as<u64>() : hit_k[1].as<u64>(), hsel ? val_v.as<u32>() : hit_v[1].as<u32>(),
                      hit_v[0].as<u32>(), hit_len.as<u32>(), n_valid, iv.as<RkInterval>(), n_iv,
-                     rk_b, own_b, rk_attempt == 0 ? 1u : 0u, scalars.as<u32>() + SC_RK_OK};
+                     rk_b, own_b, need_restart ? 1u : 0u, scalars.as<u32>() + SC_RK_OK};
     launch_rk_chain(cp, 1, st);
     u32 res[3] = {0, 0, 0};                      // n_iv, n_valid, ok (consecutive scalars)
     CKI(fetch_words(n_iv, res, 3));
-    if (rk_attempt == 0 && !res[2]) continue;    // hits too dense for a restart point: from the ring shift
+    if (need_restart && !res[2]) { done = false; return 0; }     // hits too dense for a restart point: from the ring shift
     RkExpandParams ex{g, iv.as<RkInterval>(), own_b, own_e, (mask & NLZM_MF_BT4) ? 1u : 0u, sink()};
     launch_rk_expand(ex, res[0], st);
-    return 0;
-  }
     return 0;
 }
 
@@ -1346,6 +1355,7 @@ int nlzm_mf_import_segment(nlzm_mf *mf, const nlzm_mf_segment *d, int via_ipc) {
     const bool async = (via_ipc & 0x100) != 0;           // copies go to the copy stream; the next find waits for them
     via_ipc &= 0xFF;
     cudaStream_t cst = async ? mf->st_copy : mf->st;
+    (void)cst;
     const u8 *src_el = (const u8 *)d->elems_alloc, *src_ptr = (const u8 *)d->ptrs_alloc;
     if (via_ipc == 2) {
         // elems_alloc / ptrs_alloc are HOST copies of the two slices (nlzm_mf_read_segment on the exporting side)
